@@ -1,0 +1,189 @@
+/* tbslas_b200.h -- C ABI of the B200-native semi-Lagrangian hot path.
+ *
+ * Drop-in boundary for arashb/tbslas's src/semilag + src/tree advection path
+ * (reference @ 0e66711).  The reference's "operator API" is a C++ functor concept,
+ *     void f(const real_t* pos_aos, int n, real_t* out_aos);
+ *     void f(const real_t* pos_aos, int n, real_t t, real_t* out_aos);
+ * (tree_functor.h:800-811, tree_set_functor.h:49-50, tree_extrap_functor.h:47)
+ * consumed by IntegrateRK2 / ComputeTrajRK2 / SolveSemilagRK2 (traj.h:25-44,
+ * semilag.h:21-34).  This header is what an FFI for that path binds: plain
+ * pointers and sizes, opaque handles, int status (0 = ok), no exceptions, no
+ * torch types.  The header-only C++ adaptors in include/tbslas_b200/ wrap these
+ * entry points back into the functor concept so the reference's templates and
+ * drivers compile against them unchanged.
+ *
+ * Conventions
+ *   - points are AoS [n][3] doubles, values AoS [n][dof] doubles, exactly as the
+ *     reference passes them; `mem` says whether the caller's buffers live in host
+ *     memory (copied in/out on the context's stream) or are device pointers.
+ *   - bc: TBSLAS_FREESPACE / TBSLAS_PERIODIC == pvfmm::BoundaryType, which the
+ *     reference reads implicitly from its SimConfig singleton
+ *     (tree_functor.h:174,469,803); here it is an explicit argument.
+ *   - when bc is periodic the position buffer handed to an eval call is wrapped IN
+ *     PLACE ((c<0)->c+1, (c>=1)->c-1, once), as the reference does through a
+ *     const_cast (tree_functor.h:442-449,803).
+ *   - all work is stream ordered on the context's stream; calls with host buffers
+ *     return after the results have landed, calls with device buffers return after
+ *     enqueueing (use tbslas_b200_synchronize or your own stream sync).
+ *   - one context per GPU per process; a context and its trees are not thread safe
+ *     (neither is the reference: function-static scratch, tree_functor.h:166,519).
+ *   - there is NO CPU fallback: every entry point fails with TBSLAS_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef TBSLAS_B200_H_
+#define TBSLAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tbslas_ctx tbslas_ctx;
+typedef struct tbslas_tree tbslas_tree;
+
+enum {
+  TBSLAS_OK = 0,
+  TBSLAS_ERR_INVALID = 1,     /* bad argument */
+  TBSLAS_ERR_CUDA = 2,        /* CUDA runtime / no usable device */
+  TBSLAS_ERR_COMM = 3,        /* NCCL */
+  TBSLAS_ERR_UNSUPPORTED = 4, /* e.g. Chebyshev degree out of range */
+  TBSLAS_ERR_NOMEM = 5
+};
+enum { TBSLAS_FREESPACE = 0, TBSLAS_PERIODIC = 1 };
+enum { TBSLAS_MEM_HOST = 0, TBSLAS_MEM_DEVICE = 1 };
+
+/* Velocity "functor" kinds (what the reference passes as FieldFunctor):
+ *   STEADY  tree[0]                      tbslas::NodeFieldFunctor    tree_functor.h:793-815
+ *   SET4    tree[0..3] at times[0..3]    tbslas::FieldSetFunctor     tree_set_functor.h:27-97
+ *           (cubic Hermite in time, utils/cubic.h:42-56)
+ *   EXTRAP  tree[0]=t^{n-1}, tree[1]=t^n tbslas::FieldExtrapFunctor  tree_extrap_functor.h:27-92
+ *           (1.5*v(t^n) - 0.5*v(t^{n-1})) */
+enum { TBSLAS_FIELD_STEADY = 0, TBSLAS_FIELD_SET4 = 1, TBSLAS_FIELD_EXTRAP = 2 };
+typedef struct tbslas_field {
+  int kind;
+  tbslas_tree *tree[4];
+  double times[4];
+} tbslas_field;
+
+#define TBSLAS_MAX_CHEB_DEG 16 /* reference asserts deg < 20 (cheb.h:43); scripts use <= 14 */
+
+/* ---- context ------------------------------------------------------------ */
+/* Replaces: process start-up of a reference driver (MPI_Init + SimConfig,
+ * advection.cpp:50-90).  `device` is the CUDA ordinal this process drives. */
+int tbslas_b200_init(int device, tbslas_ctx **ctx);
+int tbslas_b200_finalize(tbslas_ctx *ctx);
+/* Run on an externally owned cudaStream_t (e.g. the caller's framework stream);
+ * NULL restores the context's own stream. */
+int tbslas_b200_set_stream(tbslas_ctx *ctx, void *cuda_stream);
+int tbslas_b200_synchronize(tbslas_ctx *ctx);
+/* Last error text of this context (never NULL). */
+const char *tbslas_b200_last_error(tbslas_ctx *ctx);
+const char *tbslas_b200_version(void);
+
+/* ---- multi-GPU: one process per GPU, Morton-range shards ------------------ */
+/* Replaces: sim_config->comm / *tree->Comm() (tree_functor.h:407,570).
+ * Rank 0 obtains a 128-byte NCCL unique id and ships it to the other ranks by any
+ * means the host has (MPI_Bcast, torch.distributed, a file); every rank then calls
+ * comm_init.  Without comm_init the context is single-rank. */
+int tbslas_b200_comm_unique_id(void *id128);
+int tbslas_b200_comm_init(tbslas_ctx *ctx, int nranks, int rank, const void *id128);
+int tbslas_b200_comm_rank(tbslas_ctx *ctx, int *rank, int *nranks);
+
+/* ---- trees -------------------------------------------------------------- */
+/* Replaces: the leaf walk at tree_functor.h:417-427 (GetNodeList filtered by
+ * IsLeaf && !IsGhost) and the per-leaf reads of Coord/Depth/ChebData
+ * (:249-266,:283-284).  Leaves must be in Morton (PVFMM preorder) order.  In a
+ * multi-rank context every rank passes ITS OWN contiguous Morton range (what an MPI
+ * rank of the reference owns); the first-leaf keys are all-gathered here, replacing
+ * the per-call MPI_Allgather at tree_functor.h:433-437.
+ *   coord  [n_leaf][3]   depth [n_leaf]   coeff [n_leaf][dof][Ncoef],
+ *   Ncoef = (q+1)(q+2)(q+3)/6 in the reference's packed order (:256-266). */
+int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf,
+                            const double *coord, const uint8_t *depth,
+                            const double *coeff, int mem, tbslas_tree **tree);
+/* New coefficients on the same leaves (what SetTreeGridValues writes every step,
+ * tree_utils.h:547-550). */
+int tbslas_b200_tree_update_coeff(tbslas_tree *tree, const double *coeff, int mem);
+int tbslas_b200_tree_destroy(tbslas_tree *tree);
+int tbslas_b200_tree_info(const tbslas_tree *tree, int *q, int *dof, size_t *n_leaf);
+
+/* ---- evaluation (tbslas::EvalTree, tree_functor.h:397-690) ---------------- */
+/* out[n][dof] = field(pos[n]).  leaf_idx (optional, same memory space as pos) gets
+ * the index of the leaf that evaluated each point, counted in the GLOBAL Morton
+ * order (-1: no leaf claims the point; its value is 0).  Out-of-domain points under
+ * FREESPACE evaluate to 0 (cheb_poly is zero outside [-1,1]). */
+int tbslas_b200_eval(tbslas_tree *tree, int bc, double *pos, size_t n, double *out,
+                     int32_t *leaf_idx, int mem);
+/* FieldSetFunctor::operator() (tree_set_functor.h:49-79). */
+int tbslas_b200_eval_set4(tbslas_tree *const trees[4], const double times[4], double t,
+                          int bc, double *pos, size_t n, double *out, int mem);
+/* FieldExtrapFunctor::operator() (tree_extrap_functor.h:47-78). */
+int tbslas_b200_eval_extrap(tbslas_tree *tp, tbslas_tree *tc, int bc, double *pos,
+                            size_t n, double *out, int mem);
+/* Any field kind through one entry point (t is ignored by STEADY and EXTRAP). */
+int tbslas_b200_eval_field(const tbslas_field *f, double t, int bc, double *pos, size_t n,
+                           double *out, int mem);
+
+/* ---- trajectories and the semi-Lagrangian step ---------------------------- */
+/* tbslas::ComputeTrajRK2 (traj.inc:49-68; two-functor form :95-115): nrk explicit-
+ * midpoint sub-steps from tinit to tfinal.  f2 == NULL: both stages sample f1 (second
+ * at t + tau/2); otherwise stage 1 samples f1 and stage 2 samples f2
+ * (tree_ns.h:471-483).  pos is not modified; out_pos[n][3]. */
+int tbslas_b200_traj_rk2(const tbslas_field *f1, const tbslas_field *f2, int bc,
+                         const double *pos, size_t n, double tinit, double tfinal,
+                         int nrk, double *out_pos, int mem);
+/* tbslas::SolveSemilagRK2 (semilag.inc:27-45, :49-69): departure points over
+ * [timestep*dt, timestep*dt - dt], then `con` sampled there.  out_vals[n][dof_con];
+ * out_dep (optional) receives the departure points [n][3]. */
+int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2,
+                            tbslas_tree *con, int bc, const double *pos, size_t n,
+                            int timestep, double dt, int nrk, double *out_vals,
+                            double *out_dep, int mem);
+
+/* ---- uniform-grid cubic variant (tbslas::fast_interp, tree_functor.h:89-153) - */
+/* grid [dof][n_reg][n_reg][n_reg] (x fastest), node centred on [0,1]^3. */
+int tbslas_b200_cubic_eval(tbslas_ctx *ctx, const double *grid, int n_reg, int dof,
+                           const double *pos, size_t n, double *out, int mem);
+
+/* ---- either side of the path ("next" rows) -------------------------------- */
+/* tbslas::CollectChebTreeGridPoints (tree_utils.h:442-498): arrival points of the
+ * local leaves, leaf-major, [n_leaf*(q+1)^3][3]. */
+int tbslas_b200_collect_grid_points(tbslas_tree *tree, double *out_pos, int mem);
+/* tbslas::new_nodes (cheb.h:41-68), 1-D nodes, host only: out[q+1]. */
+int tbslas_b200_new_nodes(int q, double *out);
+
+/* ---- host-side shard logic (no GPU needed) -------------------------------- */
+/* 48-bit Morton key of a query point as EvalTree builds it (tree_functor.h:464-479):
+ * z-major interleave of floor(c * 2^15), a coordinate == 1.0 shifted by 2^-15 unless
+ * periodic; UINT64_MAX when any anchor leaves the 15-bit range. */
+uint64_t tbslas_b200_point_key(double x, double y, double z, int bc);
+/* Owner rank of a key given the first-leaf key of every rank (tree_functor.h:491-513
+ * + the split-key rule of par::SortScatterIndex, :569): last r with splitter[r] <= key
+ * (rank 0 when key < splitter[0]). */
+int tbslas_b200_owner_of_key(uint64_t key, const uint64_t *splitters, int nranks);
+/* Equal-count Morton-range partition of n_leaf leaves over nranks:
+ * first[r] = r*n_leaf/nranks, first[nranks] = n_leaf. */
+int tbslas_b200_partition_leaves(size_t n_leaf, int nranks, size_t *first);
+
+/* ---- instrumentation (pvfmm::Profile::Tic/Toc tags, tree_functor.h:463-674) -- */
+/* When enabled, every kernel stage is bracketed with CUDA events on the context's
+ * stream.  `get` synchronises and returns accumulated milliseconds and launch counts
+ * per stage since the last reset.  Stage names: see tbslas_b200_profile_stage_name. */
+int tbslas_b200_profile_enable(tbslas_ctx *ctx, int on);
+int tbslas_b200_profile_reset(tbslas_ctx *ctx);
+int tbslas_b200_profile_num_stages(void);
+const char *tbslas_b200_profile_stage_name(int stage);
+int tbslas_b200_profile_get(tbslas_ctx *ctx, int stage, double *ms, long long *launches,
+                            double *units);
+/* Total kernels launched by this context since init (the bench's gpu_launches). */
+long long tbslas_b200_kernel_launches(tbslas_ctx *ctx);
+/* Measured FP64 FMA peak of this device (a DFMA-only kernel, best of `reps`),
+ * the denominator for the evaluation kernel's roofline. */
+int tbslas_b200_fp64_peak(tbslas_ctx *ctx, int reps, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBSLAS_B200_H_ */
