@@ -67,7 +67,7 @@ typedef struct tbslas_field {
   double times[4];
 } tbslas_field;
 
-#define TBSLAS_MAX_CHEB_DEG 16 /* reference asserts deg < 20 (cheb.h:43); scripts use <= 14 */
+#define TBSLAS_MAX_CHEB_DEG 19 /* reference asserts deg < 20 (cheb.h:43); scripts use <= 14 */
 
 /* ---- context ------------------------------------------------------------ */
 /* Replaces: process start-up of a reference driver (MPI_Init + SimConfig,
@@ -75,7 +75,8 @@ typedef struct tbslas_field {
 int tbslas_b200_init(int device, tbslas_ctx **ctx);
 int tbslas_b200_finalize(tbslas_ctx *ctx);
 /* Run on an externally owned cudaStream_t (e.g. the caller's framework stream);
- * NULL restores the context's own stream. */
+ * NULL restores the context's own stream; the legacy default stream is the CUDA handle
+ * cudaStreamLegacy ((void*)1), not NULL. */
 int tbslas_b200_set_stream(tbslas_ctx *ctx, void *cuda_stream);
 int tbslas_b200_synchronize(tbslas_ctx *ctx);
 /* Last error text of this context (never NULL). */

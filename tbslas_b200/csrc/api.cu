@@ -1,0 +1,668 @@
+// C ABI of libtbslas_b200.so: context, trees and the host-side orchestration of the
+// semi-Lagrangian hot path (see include/tbslas_b200.h for the contract and the
+// reference file:line each entry point replaces).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "keys.cuh"
+
+namespace tb {
+
+int fail(tbslas_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+int ws_get(tbslas_ctx *ctx, Slot s, size_t bytes, void **out) {
+  Buf &b = ctx->ws[s];
+  if (bytes > b.cap) {
+    if (b.p) {
+      // stream-ordered users of the old block must finish before it is released
+      TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      TB_CUDA(ctx, cudaFree(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+    }
+    size_t cap = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) {
+      b.p = nullptr;
+      return fail(ctx, TBSLAS_ERR_NOMEM, "cudaMalloc(%zu bytes) for workspace %d: %s", cap, (int)s,
+                  cudaGetErrorString(e));
+    }
+    b.cap = cap;
+  }
+  *out = b.p;
+  return TBSLAS_OK;
+}
+
+StageScope::StageScope(tbslas_ctx *c, int stage, double units, int n_launch) : ctx(c) {
+  c->launches += n_launch;
+  c->acc_launch[stage] += n_launch;
+  c->acc_units[stage] += units;
+  if (!c->prof) return;
+  ProfRec r;
+  r.stage = stage;
+  r.units = units;
+  for (cudaEvent_t *e : {&r.a, &r.b}) {
+    if (!c->ev_pool.empty()) {
+      *e = c->ev_pool.back();
+      c->ev_pool.pop_back();
+    } else if (cudaEventCreate(e) != cudaSuccess) {
+      return;
+    }
+  }
+  cudaEventRecord(r.a, c->stream);
+  c->recs.push_back(r);
+  idx = (int)c->recs.size() - 1;
+}
+StageScope::~StageScope() {
+  if (idx >= 0) cudaEventRecord(ctx->recs[idx].b, ctx->stream);
+}
+
+static int prof_collect(tbslas_ctx *ctx) {
+  if (ctx->recs.empty()) return TBSLAS_OK;
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (ProfRec &r : ctx->recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) ctx->acc_ms[r.stage] += ms;
+    ctx->ev_pool.push_back(r.a);
+    ctx->ev_pool.push_back(r.b);
+  }
+  ctx->recs.clear();
+  return TBSLAS_OK;
+}
+
+static const char *kStageNames[ST_COUNT] = {"H2D",     "D2H",       "Locate", "Bin",
+                                            "ChebEval", "Combine",   "CubicGrid", "Pack",
+                                            "Exchange", "Unpack",    "GridPoints"};
+
+// multi-rank pieces (comm.cu)
+int comm_tree_splitters(tbslas_tree *t);
+int comm_eval_outsiders(tbslas_tree *t, int bc, const double *pos, size_t n, const int32_t *leaf,
+                        const uint32_t *rank, const uint32_t *send_count_dev, int epilogue,
+                        double *out, const double *base, double alpha, int32_t *leaf_out);
+void comm_destroy(tbslas_ctx *ctx);
+
+// ---------------------------------------------------------------------------
+// one tree evaluation on device buffers (tbslas::EvalTree, tree_functor.h:397-690)
+// ---------------------------------------------------------------------------
+static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int epilogue,
+                             double *out, const double *base, double alpha, int32_t *leaf_out,
+                             bool allow_exchange) {
+  tbslas_ctx *ctx = t->ctx;
+  if (n >= (size_t)0xfffffff0u)
+    return fail(ctx, TBSLAS_ERR_INVALID, "n = %zu exceeds the 32-bit point index range", n);
+  if (epilogue == EPI_AXPY && t->dof != 3)
+    return fail(ctx, TBSLAS_ERR_INVALID, "position update needs a dof-3 field (dof = %d)", t->dof);
+  const int tile_pts = eval_tile_points(t->q);
+  if (tile_pts <= 0)
+    return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "Chebyshev degree %d not supported (1..%d)", t->q,
+                TBSLAS_MAX_CHEB_DEG);
+  const size_t max_tiles = n / tile_pts + t->n_leaf + 2;
+  void *leaf, *rank, *count, *bin_start, *tile_start, *tile_map, *perm, *send_count = nullptr;
+  TB_TRY(ws_get(ctx, WS_LEAF, sizeof(int32_t) * (n + 1), &leaf));
+  TB_TRY(ws_get(ctx, WS_RANK, sizeof(uint32_t) * (n + 1), &rank));
+  TB_TRY(ws_get(ctx, WS_PERM, sizeof(uint32_t) * (n + 1), &perm));
+  TB_TRY(ws_get(ctx, WS_COUNT, sizeof(uint32_t) * (t->n_leaf + 2 + kMaxRanks), &count));
+  TB_TRY(ws_get(ctx, WS_BINSTART, sizeof(uint32_t) * (t->n_leaf + 2), &bin_start));
+  TB_TRY(ws_get(ctx, WS_TILESTART, sizeof(uint32_t) * (t->n_leaf + 2), &tile_start));
+  TB_TRY(ws_get(ctx, WS_TILELEAF, sizeof(int2) * max_tiles, &tile_map));
+  const bool multi = allow_exchange && ctx->nranks > 1;
+  if (multi) send_count = (uint32_t *)count + t->n_leaf + 2;
+
+  LocateArgs la;
+  la.tree = t;
+  la.periodic = (bc == TBSLAS_PERIODIC);
+  la.pos = pos;
+  la.n = n;
+  la.leaf = (int32_t *)leaf;
+  la.rank = (uint32_t *)rank;
+  la.count = (uint32_t *)count;
+  la.send_count = (uint32_t *)send_count;
+  TB_TRY(launch_locate(ctx, la));
+
+  BinArgs ba;
+  ba.n_leaf = t->n_leaf;
+  ba.n = n;
+  ba.tile_pts = tile_pts;
+  ba.leaf = (const int32_t *)leaf;
+  ba.rank = (const uint32_t *)rank;
+  ba.count = (const uint32_t *)count;
+  ba.bin_start = (uint32_t *)bin_start;
+  ba.tile_start = (uint32_t *)tile_start;
+  ba.tile_map = (int2 *)tile_map;
+  ba.perm = (uint32_t *)perm;
+  ba.max_tiles = max_tiles;
+  TB_TRY(launch_bin(ctx, ba));
+
+  EvalArgs ea;
+  ea.tree = t;
+  ea.pos = pos;
+  ea.n = n;
+  ea.perm = (const uint32_t *)perm;
+  ea.bin_start = (const uint32_t *)bin_start;
+  ea.tile_start = (const uint32_t *)tile_start;
+  ea.tile_map = (const int2 *)tile_map;
+  ea.max_tiles = max_tiles;
+  ea.epilogue = epilogue;
+  ea.out = out;
+  ea.base = base;
+  ea.alpha = alpha;
+  TB_TRY(launch_cheb_eval(ctx, ea));
+
+  if (leaf_out) {
+    TB_CUDA(ctx, cudaMemcpyAsync(leaf_out, leaf, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    TB_TRY(launch_leaf_fixup(ctx, leaf_out, n, t->n_leaf, t->leaf_offset));
+  }
+  if (multi)
+    TB_TRY(comm_eval_outsiders(t, bc, pos, n, (const int32_t *)leaf, (const uint32_t *)rank,
+                               (const uint32_t *)send_count, epilogue, out, base, alpha, leaf_out));
+  return TBSLAS_OK;
+}
+
+// used by comm.cu to evaluate points received from other ranks (all of them local)
+int eval_received_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out,
+                         int32_t *leaf_out) {
+  return eval_local_points(t, bc, pos, n, EPI_STORE, out, nullptr, 0.0, leaf_out, false);
+}
+
+static int eval_tree_dev(tbslas_tree *t, int bc, double *pos, size_t n, int epilogue, double *out,
+                         const double *base, double alpha, int32_t *leaf_out) {
+  return eval_local_points(t, bc, pos, n, epilogue, out, base, alpha, leaf_out, true);
+}
+
+static int check_field(tbslas_ctx **ctx_out, const tbslas_field *f, int *dof) {
+  if (!f) return TBSLAS_ERR_INVALID;
+  const int nt = f->kind == TBSLAS_FIELD_STEADY ? 1 : f->kind == TBSLAS_FIELD_SET4 ? 4
+                 : f->kind == TBSLAS_FIELD_EXTRAP ? 2 : 0;
+  if (nt == 0 || !f->tree[0]) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = f->tree[0]->ctx;
+  for (int i = 0; i < nt; i++) {
+    if (!f->tree[i] || f->tree[i]->ctx != ctx)
+      return fail(ctx, TBSLAS_ERR_INVALID, "field tree %d missing or from another context", i);
+    if (f->tree[i]->dof != f->tree[0]->dof)
+      return fail(ctx, TBSLAS_ERR_INVALID, "field trees disagree on dof");
+  }
+  *ctx_out = ctx;
+  *dof = f->tree[0]->dof;
+  return TBSLAS_OK;
+}
+
+// out = field(pos)                       (axpy == 0)
+// out = base + alpha * field(pos)        (axpy == 1; the RK2 position update)
+static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos, size_t n,
+                          double *out, int axpy, const double *base, double alpha) {
+  tbslas_ctx *ctx;
+  int dof;
+  TB_TRY(check_field(&ctx, f, &dof));
+  if (f->kind == TBSLAS_FIELD_STEADY)  // time argument ignored, tree_functor.h:808-811
+    return eval_tree_dev(f->tree[0], bc, pos, n, axpy ? EPI_AXPY : EPI_STORE, out, base, alpha,
+                         nullptr);
+  const size_t m = n * dof;
+  void *va;
+  if (f->kind == TBSLAS_FIELD_SET4) {  // tree_set_functor.h:55-72
+    TB_TRY(ws_get(ctx, WS_VAL_A, sizeof(double) * 4 * m, &va));
+    double *v4 = (double *)va;
+    for (int i = 0; i < 4; i++)
+      TB_TRY(eval_tree_dev(f->tree[i], bc, pos, n, EPI_STORE, v4 + i * m, nullptr, 0.0, nullptr));
+    return launch_cubic_time(ctx, v4, m, f->times, tq, out, base, alpha, axpy);
+  }
+  // EXTRAP: tree[0] = previous, tree[1] = current; current first (tree_extrap_functor.h:59-66)
+  TB_TRY(ws_get(ctx, WS_VAL_A, sizeof(double) * 2 * m, &va));
+  double *vc = (double *)va, *vp = vc + m;
+  TB_TRY(eval_tree_dev(f->tree[1], bc, pos, n, EPI_STORE, vc, nullptr, 0.0, nullptr));
+  TB_TRY(eval_tree_dev(f->tree[0], bc, pos, n, EPI_STORE, vp, nullptr, 0.0, nullptr));
+  return launch_extrap(ctx, vc, vp, m, out, base, alpha, axpy);
+}
+
+// tbslas::ComputeTrajRK2 on device state: xsol [n][3] in/out, xtmp [n][3] scratch.
+static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, double *xsol,
+                        double *xtmp, size_t n, double tinit, double tfinal, int nrk) {
+  const double tau = (tfinal - tinit) / nrk;  // traj.inc:55
+  double tcur = tinit;
+  for (int s = 0; s < nrk; s++) {
+    // v1 = V(x, t);  xtmp = x + 0.5*tau*v1      traj.inc:33-36 (x wrapped in place if periodic)
+    TB_TRY(eval_field_dev(f1, tcur, bc, xsol, n, xtmp, 1, xsol, 0.5 * tau));
+    // v2 = V(xtmp, t + tau/2);  x = x + tau*v2  traj.inc:40-42
+    TB_TRY(eval_field_dev(f2 ? f2 : f1, tcur + 0.5 * tau, bc, xtmp, n, xsol, 1, xsol, tau));
+    tcur = tcur + tau;
+  }
+  return TBSLAS_OK;
+}
+
+struct HostIO {  // staging of caller buffers that live in host memory
+  tbslas_ctx *ctx;
+  int mem;
+  int h2d(Slot s, const void *src, size_t bytes, void **dev) {
+    if (mem == TBSLAS_MEM_DEVICE) {
+      *dev = const_cast<void *>(src);
+      return TBSLAS_OK;
+    }
+    TB_TRY(ws_get(ctx, s, bytes, dev));
+    StageScope sc(ctx, ST_H2D, (double)bytes, 0);
+    TB_CUDA(ctx, cudaMemcpyAsync(*dev, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return TBSLAS_OK;
+  }
+  int out_buf(Slot s, void *dst, size_t bytes, void **dev) {
+    if (mem == TBSLAS_MEM_DEVICE) {
+      *dev = dst;
+      return TBSLAS_OK;
+    }
+    return ws_get(ctx, s, bytes, dev);
+  }
+  int d2h(void *dst, const void *dev, size_t bytes) {
+    if (mem == TBSLAS_MEM_DEVICE || !dst) return TBSLAS_OK;
+    StageScope sc(ctx, ST_D2H, (double)bytes, 0);
+    TB_CUDA(ctx, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return TBSLAS_OK;
+  }
+  int finish() {
+    if (mem == TBSLAS_MEM_DEVICE) return TBSLAS_OK;
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TBSLAS_OK;
+  }
+};
+
+}  // namespace tb
+
+using namespace tb;
+
+// ===========================================================================
+extern "C" {
+
+const char *tbslas_b200_version(void) { return "tbslas_b200 0.1 (sm_100a)"; }
+
+int tbslas_b200_init(int device, tbslas_ctx **out) {
+  if (!out) return TBSLAS_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TBSLAS_ERR_CUDA;
+  if (device < 0 || device >= ndev) return TBSLAS_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return TBSLAS_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TBSLAS_ERR_CUDA;
+  if (prop.major != 10) return TBSLAS_ERR_CUDA;  // sm_100a kernels only; no fallback
+  tbslas_ctx *ctx = new tbslas_ctx();
+  ctx->device = device;
+  ctx->n_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return TBSLAS_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  cudaMallocHost(&ctx->h_counts, sizeof(unsigned) * 4 * kMaxRanks);
+  *out = ctx;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_finalize(tbslas_ctx *ctx) {
+  if (!ctx) return TBSLAS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
+  for (Buf &b : ctx->ws)
+    if (b.p) cudaFree(b.p);
+  for (ProfRec &r : ctx->recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_set_stream(tbslas_ctx *ctx, void *s) {
+  if (!ctx) return TBSLAS_ERR_INVALID;
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_synchronize(tbslas_ctx *ctx) {
+  if (!ctx) return TBSLAS_ERR_INVALID;
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBSLAS_OK;
+}
+
+const char *tbslas_b200_last_error(tbslas_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// ---------------------------------------------------------------- trees
+int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, const double *coord,
+                            const uint8_t *depth, const double *coeff, int mem, tbslas_tree **out) {
+  if (!ctx || !out) return TBSLAS_ERR_INVALID;
+  *out = nullptr;
+  if (q < 1 || q > TBSLAS_MAX_CHEB_DEG)
+    return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "Chebyshev degree %d not supported (1..%d)", q,
+                TBSLAS_MAX_CHEB_DEG);
+  if (dof < 1 || dof > 16 || n_leaf < 1 || n_leaf > 0x7ffffff0u || !coord || !depth || !coeff)
+    return fail(ctx, TBSLAS_ERR_INVALID, "tree_create: bad argument (dof=%d, n_leaf=%zu)", dof, n_leaf);
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  // geometry and keys are built on the host (n_leaf is small next to the points)
+  std::vector<double> hc(3 * n_leaf);
+  std::vector<uint8_t> hd(n_leaf);
+  if (mem == TBSLAS_MEM_DEVICE) {
+    TB_CUDA(ctx, cudaMemcpy(hc.data(), coord, sizeof(double) * 3 * n_leaf, cudaMemcpyDeviceToHost));
+    TB_CUDA(ctx, cudaMemcpy(hd.data(), depth, n_leaf, cudaMemcpyDeviceToHost));
+  } else {
+    memcpy(hc.data(), coord, sizeof(double) * 3 * n_leaf);
+    memcpy(hd.data(), depth, n_leaf);
+  }
+  std::vector<uint64_t> hk(n_leaf);
+  std::vector<double4> hg(n_leaf + 1);
+  for (size_t j = 0; j < n_leaf; j++) {
+    if (hd[j] > kMaxDepth) return fail(ctx, TBSLAS_ERR_INVALID, "leaf %zu: depth %d > 15", j, hd[j]);
+    hk[j] = leaf_key(hc[3 * j], hc[3 * j + 1], hc[3 * j + 2]);
+    if (hk[j] == ~0ull) return fail(ctx, TBSLAS_ERR_INVALID, "leaf %zu: corner outside [0,1)^3", j);
+    if (j && !(hk[j - 1] < hk[j]))
+      return fail(ctx, TBSLAS_ERR_INVALID, "leaves must be in strictly ascending Morton order (leaf %zu)", j);
+    // (x - c) * 2.0 * s, s = 2^depth (tree_functor.h:285-293): 2*s is exact
+    hg[j] = make_double4(hc[3 * j], hc[3 * j + 1], hc[3 * j + 2], 2.0 * (double)(1ull << hd[j]));
+  }
+  hg[n_leaf] = make_double4(0, 0, 0, 2.0);  // null leaf: zero coefficients
+  tbslas_tree *t = new tbslas_tree();
+  t->ctx = ctx;
+  t->q = q;
+  t->dof = dof;
+  t->n_leaf = n_leaf;
+  t->ncoef = (size_t)(q + 1) * (q + 2) * (q + 3) / 6;
+  const size_t ncoef_pad = t->ncoef + (t->ncoef & 1);  // 16-byte rows for TMA / LDS.128
+  t->stride = ncoef_pad * dof;
+  auto bail = [&](int rc) {
+    tbslas_b200_tree_destroy(t);
+    return rc;
+  };
+#define TB_TREE_CUDA(call)                                                                   \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return bail(fail(ctx, TBSLAS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)));      \
+  } while (0)
+  TB_TREE_CUDA(cudaMalloc(&t->d_key, sizeof(uint64_t) * n_leaf));
+  TB_TREE_CUDA(cudaMalloc(&t->d_geom, sizeof(double4) * (n_leaf + 1)));
+  TB_TREE_CUDA(cudaMalloc(&t->d_depth, n_leaf));
+  TB_TREE_CUDA(cudaMalloc(&t->d_coeff, sizeof(double) * t->stride * (n_leaf + 1)));
+  TB_TREE_CUDA(cudaMemcpy(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice));
+  TB_TREE_CUDA(cudaMemcpy(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice));
+  TB_TREE_CUDA(cudaMemcpy(t->d_depth, hd.data(), n_leaf, cudaMemcpyHostToDevice));
+  TB_TREE_CUDA(cudaMemset(t->d_coeff, 0, sizeof(double) * t->stride * (n_leaf + 1)));
+#undef TB_TREE_CUDA
+  t->splitters.assign(1, hk[0]);
+  int rc = tbslas_b200_tree_update_coeff(t, coeff, mem);
+  if (rc != TBSLAS_OK) return bail(rc);
+  if (ctx->nranks > 1) {
+    rc = comm_tree_splitters(t);
+    if (rc != TBSLAS_OK) return bail(rc);
+  }
+  *out = t;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_tree_update_coeff(tbslas_tree *t, const double *coeff, int mem) {
+  if (!t || !coeff) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  const size_t ncoef_pad = t->stride / t->dof;
+  StageScope sc(ctx, ST_H2D, (double)(t->n_leaf * t->dof * t->ncoef * 8), 0);
+  // [leaf][dof][Ncoef] -> rows padded to an even number of doubles
+  TB_CUDA(ctx, cudaMemcpy2DAsync(t->d_coeff, ncoef_pad * sizeof(double), coeff,
+                                 t->ncoef * sizeof(double), t->ncoef * sizeof(double),
+                                 t->n_leaf * t->dof,
+                                 mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice
+                                                          : cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_tree_destroy(tbslas_tree *t) {
+  if (!t) return TBSLAS_ERR_INVALID;
+  cudaStreamSynchronize(t->ctx->stream);
+  cudaFree(t->d_key);
+  cudaFree(t->d_geom);
+  cudaFree(t->d_depth);
+  cudaFree(t->d_coeff);
+  cudaFree(t->d_splitters);
+  delete t;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_tree_info(const tbslas_tree *t, int *q, int *dof, size_t *n_leaf) {
+  if (!t) return TBSLAS_ERR_INVALID;
+  if (q) *q = t->q;
+  if (dof) *dof = t->dof;
+  if (n_leaf) *n_leaf = t->n_leaf;
+  return TBSLAS_OK;
+}
+
+// ---------------------------------------------------------------- evaluation
+int tbslas_b200_eval_field(const tbslas_field *f, double tq, int bc, double *pos, size_t n,
+                           double *out, int mem) {
+  tbslas_ctx *ctx;
+  int dof;
+  TB_TRY(check_field(&ctx, f, &dof));
+  if (n && (!pos || !out)) return fail(ctx, TBSLAS_ERR_INVALID, "null buffer");
+  HostIO io{ctx, mem};
+  void *dpos, *dout;
+  TB_TRY(io.h2d(WS_POS_A, pos, sizeof(double) * 3 * n, &dpos));
+  TB_TRY(io.out_buf(WS_VAL_B, out, sizeof(double) * dof * n, &dout));
+  TB_TRY(eval_field_dev(f, tq, bc, (double *)dpos, n, (double *)dout, 0, nullptr, 0.0));
+  TB_TRY(io.d2h(out, dout, sizeof(double) * dof * n));
+  if (bc == TBSLAS_PERIODIC) TB_TRY(io.d2h(pos, dpos, sizeof(double) * 3 * n));  // wrapped in place
+  return io.finish();
+}
+
+int tbslas_b200_eval(tbslas_tree *t, int bc, double *pos, size_t n, double *out, int32_t *leaf_idx,
+                     int mem) {
+  if (!t) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  if (n && (!pos || !out)) return fail(ctx, TBSLAS_ERR_INVALID, "null buffer");
+  HostIO io{ctx, mem};
+  void *dpos, *dout, *dleaf = nullptr;
+  TB_TRY(io.h2d(WS_POS_A, pos, sizeof(double) * 3 * n, &dpos));
+  TB_TRY(io.out_buf(WS_VAL_B, out, sizeof(double) * t->dof * n, &dout));
+  if (leaf_idx) TB_TRY(io.out_buf(WS_LEAFOUT, leaf_idx, sizeof(int32_t) * n, &dleaf));
+  TB_TRY(eval_tree_dev(t, bc, (double *)dpos, n, EPI_STORE, (double *)dout, nullptr, 0.0,
+                       (int32_t *)dleaf));
+  TB_TRY(io.d2h(out, dout, sizeof(double) * t->dof * n));
+  if (leaf_idx) TB_TRY(io.d2h(leaf_idx, dleaf, sizeof(int32_t) * n));
+  if (bc == TBSLAS_PERIODIC) TB_TRY(io.d2h(pos, dpos, sizeof(double) * 3 * n));
+  return io.finish();
+}
+
+int tbslas_b200_eval_set4(tbslas_tree *const trees[4], const double times[4], double tq, int bc,
+                          double *pos, size_t n, double *out, int mem) {
+  if (!trees || !times) return TBSLAS_ERR_INVALID;
+  tbslas_field f;
+  f.kind = TBSLAS_FIELD_SET4;
+  for (int i = 0; i < 4; i++) {
+    f.tree[i] = trees[i];
+    f.times[i] = times[i];
+  }
+  return tbslas_b200_eval_field(&f, tq, bc, pos, n, out, mem);
+}
+
+int tbslas_b200_eval_extrap(tbslas_tree *tp, tbslas_tree *tc, int bc, double *pos, size_t n,
+                            double *out, int mem) {
+  tbslas_field f;
+  memset(&f, 0, sizeof(f));
+  f.kind = TBSLAS_FIELD_EXTRAP;
+  f.tree[0] = tp;
+  f.tree[1] = tc;
+  return tbslas_b200_eval_field(&f, 0.0, bc, pos, n, out, mem);
+}
+
+int tbslas_b200_traj_rk2(const tbslas_field *f1, const tbslas_field *f2, int bc, const double *pos,
+                         size_t n, double tinit, double tfinal, int nrk, double *out_pos, int mem) {
+  tbslas_ctx *ctx, *ctx2;
+  int dof, dof2;
+  TB_TRY(check_field(&ctx, f1, &dof));
+  if (f2) {
+    TB_TRY(check_field(&ctx2, f2, &dof2));
+    if (ctx2 != ctx || dof2 != dof) return fail(ctx, TBSLAS_ERR_INVALID, "f1/f2 mismatch");
+  }
+  if (dof != 3) return fail(ctx, TBSLAS_ERR_INVALID, "velocity field must have dof 3 (got %d)", dof);
+  if (nrk < 1 || (n && (!pos || !out_pos))) return fail(ctx, TBSLAS_ERR_INVALID, "bad argument");
+  HostIO io{ctx, mem};
+  void *xsol, *xtmp;
+  TB_TRY(io.out_buf(WS_POS_A, out_pos, sizeof(double) * 3 * n, &xsol));
+  TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * n, &xtmp));
+  // xsol = xinit (traj.inc:57-58)
+  {
+    StageScope sc(ctx, mem == TBSLAS_MEM_HOST ? ST_H2D : ST_COMBINE, (double)(24 * n), 0);
+    TB_CUDA(ctx, cudaMemcpyAsync(xsol, pos, sizeof(double) * 3 * n,
+                                 mem == TBSLAS_MEM_HOST ? cudaMemcpyHostToDevice
+                                                        : cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+  }
+  TB_TRY(traj_rk2_dev(f1, f2, bc, (double *)xsol, (double *)xtmp, n, tinit, tfinal, nrk));
+  TB_TRY(io.d2h(out_pos, xsol, sizeof(double) * 3 * n));
+  return io.finish();
+}
+
+int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2, tbslas_tree *con, int bc,
+                            const double *pos, size_t n, int timestep, double dt, int nrk,
+                            double *out_vals, double *out_dep, int mem) {
+  tbslas_ctx *ctx, *ctx2;
+  int dof, dof2;
+  TB_TRY(check_field(&ctx, f1, &dof));
+  if (f2) {
+    TB_TRY(check_field(&ctx2, f2, &dof2));
+    if (ctx2 != ctx || dof2 != dof) return fail(ctx, TBSLAS_ERR_INVALID, "f1/f2 mismatch");
+  }
+  if (dof != 3) return fail(ctx, TBSLAS_ERR_INVALID, "velocity field must have dof 3 (got %d)", dof);
+  if (!con || con->ctx != ctx) return fail(ctx, TBSLAS_ERR_INVALID, "advected tree missing");
+  if (nrk < 1 || (n && (!pos || !out_vals))) return fail(ctx, TBSLAS_ERR_INVALID, "bad argument");
+  const double tinit = timestep * dt;   // semilag.inc:34-35
+  const double tfinal = tinit - dt;
+  HostIO io{ctx, mem};
+  void *xsol, *xtmp, *dval;
+  if (mem == TBSLAS_MEM_DEVICE && out_dep)
+    xsol = out_dep;
+  else
+    TB_TRY(ws_get(ctx, WS_POS_A, sizeof(double) * 3 * n, &xsol));
+  TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * n, &xtmp));
+  TB_TRY(io.out_buf(WS_VAL_B, out_vals, sizeof(double) * con->dof * n, &dval));
+  {
+    StageScope sc(ctx, mem == TBSLAS_MEM_HOST ? ST_H2D : ST_COMBINE, (double)(24 * n), 0);
+    TB_CUDA(ctx, cudaMemcpyAsync(xsol, pos, sizeof(double) * 3 * n,
+                                 mem == TBSLAS_MEM_HOST ? cudaMemcpyHostToDevice
+                                                        : cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+  }
+  TB_TRY(traj_rk2_dev(f1, f2, bc, (double *)xsol, (double *)xtmp, n, tinit, tfinal, nrk));
+  if (mem == TBSLAS_MEM_HOST && out_dep) {
+    // the departure points as ComputeTrajRK2 returns them, before the scalar evaluation
+    // wraps them (semilag.inc:40-43)
+    TB_TRY(io.d2h(out_dep, xsol, sizeof(double) * 3 * n));
+  } else if (mem == TBSLAS_MEM_DEVICE && out_dep && bc == TBSLAS_PERIODIC) {
+    // keep the caller's departure points un-wrapped: evaluate on a copy
+    TB_CUDA(ctx, cudaMemcpyAsync(xtmp, xsol, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    xsol = xtmp;
+  }
+  TB_TRY(eval_tree_dev(con, bc, (double *)xsol, n, EPI_STORE, (double *)dval, nullptr, 0.0, nullptr));
+  TB_TRY(io.d2h(out_vals, dval, sizeof(double) * con->dof * n));
+  return io.finish();
+}
+
+// ---------------------------------------------------------------- cubic grid
+int tbslas_b200_cubic_eval(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, const double *pos,
+                           size_t n, double *out, int mem) {
+  if (!ctx) return TBSLAS_ERR_INVALID;
+  if (n_reg < 4 || dof < 1 || !grid || (n && (!pos || !out)))
+    return fail(ctx, TBSLAS_ERR_INVALID, "cubic_eval: bad argument (n_reg=%d, dof=%d)", n_reg, dof);
+  HostIO io{ctx, mem};
+  void *dgrid, *dpos, *dout;
+  TB_TRY(io.h2d(WS_GRID, grid, sizeof(double) * dof * (size_t)n_reg * n_reg * n_reg, &dgrid));
+  TB_TRY(io.h2d(WS_POS_A, pos, sizeof(double) * 3 * n, &dpos));
+  TB_TRY(io.out_buf(WS_VAL_B, out, sizeof(double) * dof * n, &dout));
+  TB_TRY(launch_cubic_grid(ctx, (const double *)dgrid, n_reg, dof, (const double *)dpos, n,
+                           (double *)dout));
+  TB_TRY(io.d2h(out, dout, sizeof(double) * dof * n));
+  return io.finish();
+}
+
+// ---------------------------------------------------------------- next rows
+int tbslas_b200_collect_grid_points(tbslas_tree *t, double *out_pos, int mem) {
+  if (!t || !out_pos) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  const size_t d = t->q + 1, n = t->n_leaf * d * d * d;
+  HostIO io{ctx, mem};
+  void *dout;
+  TB_TRY(io.out_buf(WS_POS_C, out_pos, sizeof(double) * 3 * n, &dout));
+  TB_TRY(launch_grid_points(ctx, t, (double *)dout));
+  TB_TRY(io.d2h(out_pos, dout, sizeof(double) * 3 * n));
+  return io.finish();
+}
+
+int tbslas_b200_new_nodes(int q, double *out) {
+  if (q < 0 || q > TBSLAS_MAX_CHEB_DEG || !out) return TBSLAS_ERR_INVALID;
+  tb::new_nodes_host(q, out);
+  return TBSLAS_OK;
+}
+
+// ---------------------------------------------------------------- host shard logic
+uint64_t tbslas_b200_point_key(double x, double y, double z, int bc) {
+  return point_key(x, y, z, bc == TBSLAS_PERIODIC);
+}
+
+int tbslas_b200_owner_of_key(uint64_t key, const uint64_t *splitters, int nranks) {
+  int owner = 0;
+  for (int r = 1; r < nranks; r++)
+    if (splitters[r] <= key) owner = r;
+  return owner;
+}
+
+int tbslas_b200_partition_leaves(size_t n_leaf, int nranks, size_t *first) {
+  if (nranks < 1 || !first) return TBSLAS_ERR_INVALID;
+  for (int r = 0; r <= nranks; r++) first[r] = (size_t)r * n_leaf / nranks;
+  return TBSLAS_OK;
+}
+
+// ---------------------------------------------------------------- instrumentation
+int tbslas_b200_profile_enable(tbslas_ctx *ctx, int on) {
+  if (!ctx) return TBSLAS_ERR_INVALID;
+  TB_TRY(prof_collect(ctx));
+  ctx->prof = on != 0;
+  return TBSLAS_OK;
+}
+int tbslas_b200_profile_reset(tbslas_ctx *ctx) {
+  if (!ctx) return TBSLAS_ERR_INVALID;
+  TB_TRY(prof_collect(ctx));
+  for (int s = 0; s < ST_COUNT; s++) {
+    ctx->acc_ms[s] = 0;
+    ctx->acc_units[s] = 0;
+    ctx->acc_launch[s] = 0;
+  }
+  return TBSLAS_OK;
+}
+int tbslas_b200_profile_num_stages(void) { return ST_COUNT; }
+const char *tbslas_b200_profile_stage_name(int s) {
+  return (s >= 0 && s < ST_COUNT) ? kStageNames[s] : "";
+}
+int tbslas_b200_profile_get(tbslas_ctx *ctx, int stage, double *ms, long long *launches, double *units) {
+  if (!ctx || stage < 0 || stage >= ST_COUNT) return TBSLAS_ERR_INVALID;
+  TB_TRY(prof_collect(ctx));
+  if (ms) *ms = ctx->acc_ms[stage];
+  if (launches) *launches = ctx->acc_launch[stage];
+  if (units) *units = ctx->acc_units[stage];
+  return TBSLAS_OK;
+}
+long long tbslas_b200_kernel_launches(tbslas_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int tbslas_b200_fp64_peak(tbslas_ctx *ctx, int reps, double *tflops) {
+  if (!ctx || !tflops) return TBSLAS_ERR_INVALID;
+  return run_fp64_peak(ctx, reps < 1 ? 1 : reps, tflops);
+}
+
+}  // extern "C"

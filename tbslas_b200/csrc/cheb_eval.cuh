@@ -1,0 +1,245 @@
+// Tensor-product Chebyshev evaluation of one leaf's polynomial at the points binned
+// into that leaf.
+//
+// Replaces tbslas::EvalNodesLocal steps d-e (reference src/tree/tree_functor.h:248-383):
+// coefficient unpack (:248-268), rescale to [-1,1] (:283-294), pvfmm::cheb_poly
+// (:328-330), pvfmm::vec_eval (:27-84) and the AoS store (:376-383); optionally fused
+// with the RK2 position update of tbslas::IntegrateRK2 (src/semilag/traj.inc:34-42).
+//
+// Design (B200, measured in profiles/r01_microbench_fp64_lds.txt):
+//   * FP64-pipe bound: Ncoef + d(d+1)/2 + d DFMA per point per dof.  DFMA issues every
+//     2 cycles per sub-partition with 8 cycles latency -> >= 4 independent chains.
+//   * A warp-broadcast LDS.64 costs 1 SM-cycle, a warp DFMA 0.5: every coefficient read
+//     from shared memory must feed >= 3-4 DFMAs, so each thread owns PPT points and the
+//     T_k(x), T_j(y) of all of them live in registers (loops fully unrolled per degree);
+//     T_i(z) is carried by its recurrence along the outer loop.
+//   * One CTA = one (leaf, tile of THREADS*PPT points).  The leaf's contiguous
+//     coefficient block (dof * Ncoef doubles, 1.3-23 KB) is staged into shared memory
+//     by ONE bulk-TMA copy (cp.async.bulk + mbarrier) issued by thread 0 while all
+//     threads gather their points and build the bases.
+//   * Points are read through the leaf grouping (perm) and results scattered back to the
+//     caller's AoS order; runs of 32 consecutive slots are consecutive points.
+// Arithmetic parity: local coordinates and the Chebyshev recurrences use separate
+// multiply/subtract exactly as the reference (bit-identical bases); the triangular
+// contraction uses FMA (the reference: mul then add), so values differ from the CPU
+// path only by rounding of the accumulation (<< 1e-12 relative to the field scale).
+#pragma once
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int kEvalThreads = 128;
+
+struct EvalParams {
+  const double *coeff;   // [(n_leaf+1)][dof][ncoef_pad]
+  const double4 *geom;   // [(n_leaf+1)] {cx,cy,cz,2*2^depth}
+  unsigned stride;       // doubles per leaf block = dof * ncoef_pad
+  unsigned ncoef_pad;
+  int dof;
+  int n_bins;            // n_leaf + 1
+  const double *pos;
+  const uint32_t *perm;
+  const uint32_t *bin_start;
+  const uint32_t *tile_start;
+  const int2 *tile_map;
+  double *out;
+  const double *base;
+  double alpha;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// 1-D bulk TMA: global -> shared, completion counted in bytes on the mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// T_0..T_Q at xi, pvfmm::cheb_poly semantics: all zero when |xi| > 1; recurrence with
+// separate multiply and subtract (bit-identical to the CPU path).
+template <int Q>
+__device__ __forceinline__ void cheb_basis(double xi, double (&T)[Q + 1]) {
+  const bool in = fabs(xi) <= 1.0;
+  const double x = in ? xi : 0.0;
+  T[0] = in ? 1.0 : 0.0;
+  if (Q >= 1) T[1] = x;
+  const double x2 = 2.0 * x;
+#pragma unroll
+  for (int i = 2; i <= Q; i++) T[i] = __dsub_rn(__dmul_rn(x2, T[i - 1]), T[i - 2]);
+}
+
+template <int Q, int PPT, int EPI>
+__global__ void __launch_bounds__(kEvalThreads)
+cheb_eval_kernel(const EvalParams p) {
+  constexpr int D = Q + 1;
+  extern __shared__ __align__(128) double s_coef[];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const unsigned n_tiles = __ldg(p.tile_start + p.n_bins);
+  if (blockIdx.x >= n_tiles) return;
+  const int2 tile = __ldg(p.tile_map + blockIdx.x);
+  const int leaf = tile.x;
+  const unsigned slot0 = (unsigned)tile.y;
+  const unsigned bin_end = __ldg(p.bin_start + leaf + 1);
+  const unsigned cnt = min((unsigned)(kEvalThreads * PPT), bin_end - slot0);
+
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = p.stride * 8u;
+    mbar_expect_tx(&s_bar, bytes);
+    tma_bulk_g2s(s_coef, p.coeff + (size_t)leaf * p.stride, bytes, &s_bar);
+  }
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned wbase = warp * 32 * PPT;
+  if (wbase >= cnt) return;  // whole warp has no points (no barrier follows)
+
+  const double4 g = p.geom[leaf];
+  unsigned idx[PPT];
+  bool ok[PPT];
+  double px[PPT][D], py[PPT][D], zc[PPT], z0[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; s++) {
+    const unsigned slot = wbase + s * 32 + lane;
+    ok[s] = slot < cnt;
+    idx[s] = __ldg(p.perm + slot0 + (ok[s] ? slot : 0u));
+    const double *x = p.pos + 3 * (size_t)idx[s];
+    // xi = (x - c) * 2 * 2^depth - 1, left to right (tree_functor.h:288-293); the
+    // power-of-two scalings are exact, so one multiply by 2*2^depth is the same value.
+    const double xi = __dadd_rn(__dmul_rn(__dsub_rn(x[0], g.x), g.w), -1.0);
+    const double yi = __dadd_rn(__dmul_rn(__dsub_rn(x[1], g.y), g.w), -1.0);
+    const double zi = __dadd_rn(__dmul_rn(__dsub_rn(x[2], g.z), g.w), -1.0);
+    cheb_basis<Q>(xi, px[s]);
+    cheb_basis<Q>(yi, py[s]);
+    const bool inz = fabs(zi) <= 1.0;
+    zc[s] = inz ? zi : 0.0;
+    z0[s] = inz ? 1.0 : 0.0;
+  }
+
+  mbar_wait(&s_bar, 0);
+
+#pragma unroll 1
+  for (int l = 0; l < p.dof; l++) {
+    const double2 *C2 = reinterpret_cast<const double2 *>(s_coef + l * p.ncoef_pad);
+    double u[PPT], tz0[PPT], tz1[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) u[s] = 0.0;
+    double2 cc = make_double2(0.0, 0.0);
+    int ci = 0;  // compile-time after unrolling
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      double pz[PPT], v[PPT];
+#pragma unroll
+      for (int s = 0; s < PPT; s++) {
+        if (i == 0)
+          pz[s] = z0[s];
+        else if (i == 1)
+          pz[s] = zc[s];
+        else
+          pz[s] = __dsub_rn(__dmul_rn(2.0 * zc[s], tz1[s]), tz0[s]);
+        tz0[s] = (i == 0) ? 0.0 : tz1[s];
+        tz1[s] = pz[s];
+        v[s] = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < D - i; j++) {
+        double w[PPT];
+#pragma unroll
+        for (int s = 0; s < PPT; s++) w[s] = 0.0;
+#pragma unroll
+        for (int k = 0; k < D - i - j; k++) {
+          if ((ci & 1) == 0) cc = C2[ci >> 1];
+          const double c = (ci & 1) ? cc.y : cc.x;
+          ci++;
+#pragma unroll
+          for (int s = 0; s < PPT; s++) w[s] = fma(px[s][k], c, w[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < PPT; s++) v[s] = fma(py[s][j], w[s], v[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < PPT; s++) u[s] = fma(pz[s], v[s], u[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+      if (ok[s]) {
+        if (EPI == EPI_STORE) {
+          p.out[(size_t)idx[s] * p.dof + l] = u[s];
+        } else {  // x' = x0 + alpha * v, multiply then add as traj.inc:36,42
+          const size_t o = 3 * (size_t)idx[s] + l;
+          p.out[o] = __dadd_rn(p.base[o], __dmul_rn(p.alpha, u[s]));
+        }
+      }
+    }
+  }
+}
+
+template <int Q, int PPT>
+int launch_cheb_eval_q(tbslas_ctx *ctx, const EvalArgs &a) {
+  const tbslas_tree *t = a.tree;
+  EvalParams p;
+  p.coeff = t->d_coeff;
+  p.geom = t->d_geom;
+  p.stride = (unsigned)t->stride;
+  p.ncoef_pad = (unsigned)(t->stride / t->dof);
+  p.dof = t->dof;
+  p.n_bins = (int)t->n_leaf + 1;
+  p.pos = a.pos;
+  p.perm = a.perm;
+  p.bin_start = a.bin_start;
+  p.tile_start = a.tile_start;
+  p.tile_map = a.tile_map;
+  p.out = a.out;
+  p.base = a.base;
+  p.alpha = a.alpha;
+  const size_t smem = t->stride * sizeof(double);
+  const unsigned grid = (unsigned)a.max_tiles;
+  if (grid == 0) return TBSLAS_OK;
+  if (a.epilogue == EPI_STORE) {
+    auto k = cheb_eval_kernel<Q, PPT, EPI_STORE>;
+    if (smem > 48 * 1024)
+      TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kEvalThreads, smem, ctx->stream>>>(p);
+  } else {
+    auto k = cheb_eval_kernel<Q, PPT, EPI_AXPY>;
+    if (smem > 48 * 1024)
+      TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kEvalThreads, smem, ctx->stream>>>(p);
+  }
+  TB_CUDA(ctx, cudaGetLastError());
+  return TBSLAS_OK;
+}
+
+// points per thread for each degree (register budget: 2*(Q+1)*PPT doubles of bases)
+constexpr int eval_ppt(int q) { return q <= 9 ? 4 : (q <= 12 ? 3 : 2); }
+
+}  // namespace tb

@@ -1,0 +1,202 @@
+// Internal declarations shared by the translation units of libtbslas_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "tbslas_b200.h"
+
+namespace tb {
+
+constexpr int kMaxDepth = 15;  // pvfmm MAX_DEPTH (reference sim_config.h:40)
+constexpr int kMaxRanks = 64;
+
+// Profiling stages; names mirror the reference's pvfmm::Profile tags where one exists
+// (tree_functor.h:463 LclHQSort, :585/:674 Out/InEvaluation, :568-593 OutScatter*).
+enum Stage {
+  ST_H2D = 0,
+  ST_D2H,
+  ST_LOCATE,    // wrap + key + leaf search + histogram   (reference: LclHQSort + part_indx)
+  ST_BIN,       // scan + tile map + scatter of point ids  (reference: the sort's permutation)
+  ST_CHEB_EVAL, // tensor-Chebyshev evaluation             (reference: In/OutEvaluation)
+  ST_COMBINE,   // cubic-in-time / extrapolation / axpy    (tree_set_functor.h:66-72)
+  ST_CUBIC,     // uniform-grid cubic interpolation        (fast_interp)
+  ST_PACK,      // bucket outsider points by owner         (OutScatterIndex)
+  ST_EXCHANGE,  // NCCL all-to-all-v                       (OutScatterForward/Reverse)
+  ST_UNPACK,
+  ST_GRIDPTS,   // arrival point generation                (CollectChebTreeGridPoints)
+  ST_COUNT
+};
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+// Workspace slots (grown on demand, freed at finalize; the reference keeps
+// function-static vectors for the same purpose, tree_functor.h:166,519-520).
+enum Slot {
+  WS_LEAF = 0,   // int32  [n]
+  WS_RANK,       // uint32 [n]
+  WS_PERM,       // uint32 [n]
+  WS_COUNT,      // uint32 [L+2]
+  WS_BINSTART,   // uint32 [L+2]
+  WS_TILESTART,  // uint32 [L+2]
+  WS_TILELEAF,   // int2   [ntile_max]
+  WS_POS_A,      // double [3n]   host-call staging / RK2 state
+  WS_POS_B,
+  WS_POS_C,
+  WS_VAL_A,      // double [n*dof] (x4 for set4)
+  WS_VAL_B,
+  WS_LEAFOUT,    // int32 [n] staging for host leaf_idx
+  WS_GRID,       // cubic grid staging
+  WS_SEND,       // exchange buffers
+  WS_RECV,
+  WS_SENDVAL,
+  WS_RECVVAL,
+  WS_SENDIDX,
+  WS_MISC,
+  WS_COUNT_SLOTS
+};
+
+struct ProfRec {
+  int stage;
+  cudaEvent_t a, b;
+  double units;
+};
+
+}  // namespace tb
+
+struct tbslas_ctx {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  tb::Buf ws[tb::WS_COUNT_SLOTS];
+  // profiling
+  bool prof = false;
+  std::vector<tb::ProfRec> recs;
+  std::vector<cudaEvent_t> ev_pool;
+  double acc_ms[tb::ST_COUNT] = {0};
+  double acc_units[tb::ST_COUNT] = {0};
+  long long acc_launch[tb::ST_COUNT] = {0};
+  long long launches = 0;
+  // communicator (single rank unless comm_init was called)
+  int rank = 0, nranks = 1;
+  void *nccl_comm = nullptr;
+  // pinned host scratch for small device->host reads (exchange counts)
+  unsigned *h_counts = nullptr;
+};
+
+struct tbslas_tree {
+  tbslas_ctx *ctx = nullptr;
+  int q = 0, dof = 0;
+  size_t n_leaf = 0;       // local leaves
+  size_t ncoef = 0;        // (q+1)(q+2)(q+3)/6
+  size_t stride = 0;       // doubles per leaf coefficient block (dof*ncoef padded to even)
+  uint64_t *d_key = nullptr;   // [n_leaf]   interleaved anchor keys, ascending
+  double4 *d_geom = nullptr;   // [n_leaf+1] {cx, cy, cz, 2*2^depth}; [n_leaf] = null leaf
+  uint8_t *d_depth = nullptr;  // [n_leaf]
+  double *d_coeff = nullptr;   // [(n_leaf+1)*stride]; block n_leaf is all zero (null leaf)
+  // Morton-range sharding (nranks > 1)
+  long long leaf_offset = 0;                 // global index of local leaf 0
+  std::vector<uint64_t> splitters;           // first leaf key of every rank
+  uint64_t *d_splitters = nullptr;
+};
+
+namespace tb {
+
+int fail(tbslas_ctx *ctx, int code, const char *fmt, ...);
+int ws_get(tbslas_ctx *ctx, Slot s, size_t bytes, void **out);
+
+struct StageScope {  // CUDA-event bracket of one stage on the context's stream
+  tbslas_ctx *ctx;
+  int idx = -1;
+  StageScope(tbslas_ctx *c, int stage, double units, int n_launch);
+  ~StageScope();
+};
+
+#define TB_CUDA(ctx, call)                                                          \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess)                                                          \
+      return tb::fail((ctx), TBSLAS_ERR_CUDA, "%s: %s (%s:%d)", #call,              \
+                      cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+  } while (0)
+
+#define TB_TRY(expr)                \
+  do {                              \
+    int rc_ = (expr);               \
+    if (rc_ != TBSLAS_OK) return rc_; \
+  } while (0)
+
+// ---- stage launchers (each enqueues on ctx->stream) ---------------------------
+// locate.cu
+struct LocateArgs {
+  const tbslas_tree *tree;
+  int periodic;
+  double *pos;            // [n][3], wrapped in place when periodic
+  size_t n;
+  int32_t *leaf;          // [n] local leaf index, n_leaf = null leaf, <= -2: outsider of rank -2-v
+  uint32_t *rank;         // [n] position inside its leaf bin (or send bucket)
+  uint32_t *count;        // [n_leaf+2] zeroed by the launcher
+  uint32_t *send_count;   // [nranks] (multi-rank only, zeroed by the launcher) or nullptr
+};
+int launch_locate(tbslas_ctx *ctx, const LocateArgs &a);
+// scan of bin counts, tile map, scatter of point ids
+struct BinArgs {
+  size_t n_leaf;          // bins 0..n_leaf (n_leaf = null leaf)
+  size_t n;
+  int tile_pts;           // points per evaluation tile
+  const int32_t *leaf;
+  const uint32_t *rank;
+  const uint32_t *count;
+  uint32_t *bin_start;    // [n_leaf+2]
+  uint32_t *tile_start;   // [n_leaf+2]; tile_start[n_leaf+1] = number of tiles
+  int2 *tile_map;         // [max_tiles] {leaf, first slot}
+  uint32_t *perm;         // [n] point ids grouped by leaf
+  size_t max_tiles;
+};
+int launch_bin(tbslas_ctx *ctx, const BinArgs &a);
+
+// cheb_eval_*.cu
+enum Epilogue { EPI_STORE = 0, EPI_AXPY = 1 };
+struct EvalArgs {
+  const tbslas_tree *tree;
+  const double *pos;       // [n][3]
+  size_t n;                // only used for accounting
+  const uint32_t *perm;
+  const uint32_t *bin_start;
+  const uint32_t *tile_start;  // [n_leaf+2], last entry = number of tiles
+  const int2 *tile_map;
+  size_t max_tiles;
+  int epilogue;
+  double *out;             // STORE: [n][dof]; AXPY: [n][3] = base + alpha*value (dof must be 3)
+  const double *base;
+  double alpha;
+};
+int eval_tile_points(int q);  // points per tile the eval kernel for degree q consumes
+int launch_cheb_eval(tbslas_ctx *ctx, const EvalArgs &a);
+
+// combine.cu
+int launch_cubic_time(tbslas_ctx *ctx, const double *v4 /*[4][m]*/, size_t m, const double times[4],
+                      double t, double *out, const double *base, double alpha, int axpy);
+int launch_extrap(tbslas_ctx *ctx, const double *vc, const double *vp, size_t m, double *out,
+                  const double *base, double alpha, int axpy);
+int launch_axpy(tbslas_ctx *ctx, const double *base, const double *v, double alpha, size_t m,
+                double *out);
+int launch_leaf_fixup(tbslas_ctx *ctx, int32_t *leaf, size_t n, size_t n_leaf, long long offset);
+// cubic_grid.cu
+int launch_cubic_grid(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, const double *pos,
+                      size_t n, double *out);
+// gridpts.cu
+int launch_grid_points(tbslas_ctx *ctx, const tbslas_tree *t, double *out);
+void new_nodes_host(int q, double *x);  // tbslas::new_nodes 1-D table (host libm)
+// peak.cu
+int run_fp64_peak(tbslas_ctx *ctx, int reps, double *tflops);
+
+}  // namespace tb

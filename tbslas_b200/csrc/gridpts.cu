@@ -1,0 +1,58 @@
+// Arrival points of a tree's leaves: tbslas::CollectChebTreeGridPoints (reference
+// src/tree/tree_utils.h:442-498) over tbslas::new_nodes (src/utils/cheb.h:41-68).
+// out[(leaf*P + i)*3 + a] = coord[leaf][a] + 2^-depth * node[i][a], leaf-major,
+// node grid x fastest.  The 1-D node table is computed on the host with the same libm
+// cos() the CPU path uses, so the points are bit-identical; the kernel is a pure
+// streaming write (24 B/point).
+#include <cmath>
+
+#include "common.cuh"
+
+namespace tb {
+
+struct Nodes1D {
+  double x[TBSLAS_MAX_CHEB_DEG + 1];
+};
+
+void new_nodes_host(int q, double *x) {  // cheb.h:51-58
+  const unsigned d = q + 1;
+  const double pi = 3.14159265358979323846264338327950288;
+  volatile double scal = 1.0 / std::cos(0.5 * pi / d);
+  for (unsigned i = 0; i < d; i++) {
+    volatile double a = (i + 0.5) * pi;
+    volatile double b = a / d;
+    volatile double c = -std::cos(b);
+    volatile double e = c * scal;
+    volatile double f = e * 0.5;
+    x[i] = f + 0.5;
+  }
+}
+
+__global__ void grid_points_kernel(const double4 *__restrict__ geom, const uint8_t *__restrict__ depth,
+                                   size_t n_leaf, int d, Nodes1D nodes, double *__restrict__ out) {
+  const size_t P = (size_t)d * d * d;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per scalar
+  if (i >= n_leaf * P * 3) return;
+  const size_t leaf = i / (3 * P);
+  const unsigned r = (unsigned)(i - leaf * 3 * P);
+  const unsigned pt = r / 3, a = r - 3 * pt;
+  const unsigned ix = (a == 0) ? pt % d : (a == 1) ? (pt / d) % d : pt / (d * d);
+  const double4 g = geom[leaf];
+  const double c = (a == 0) ? g.x : (a == 1) ? g.y : g.z;
+  const double len = 1.0 / (double)(1u << depth[leaf]);  // pow(0.5, depth), exact
+  out[i] = __dadd_rn(c, __dmul_rn(len, nodes.x[ix]));
+}
+
+int launch_grid_points(tbslas_ctx *ctx, const tbslas_tree *t, double *out) {
+  const int d = t->q + 1;
+  const size_t total = t->n_leaf * (size_t)d * d * d * 3;
+  StageScope sc(ctx, ST_GRIDPTS, (double)(total / 3), 1);
+  Nodes1D nodes;
+  new_nodes_host(t->q, nodes.x);
+  grid_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+      t->d_geom, t->d_depth, t->n_leaf, d, nodes, out);
+  TB_CUDA(ctx, cudaGetLastError());
+  return TBSLAS_OK;
+}
+
+}  // namespace tb

@@ -1,0 +1,292 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Bars (BASELINE.json north_star):
+  * leaf assignment of every point: BIT-EXACT;
+  * interpolated values: within 1e-12 relative in FP64.  "Relative" is taken against the
+    field scale of the batch (max |value|), because tensor-Chebyshev sums cancel and a
+    per-point relative bound is unattainable near zeros (last item);
+    the only arithmetic difference to the CPU path is FMA vs mul+add in the accumulation;
+  * positions after periodic wrap, cubic-grid values, time interpolation/extrapolation of
+    equal inputs, arrival points: BIT-EXACT (same operation order, un-fused).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from tbslas_b200 import flat_tree as ftm
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def rel_err(a, b):
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+def _tree(g, prefix="tree"):
+    return ftm.FlatTree(int(g[prefix + "_q"]), int(g[prefix + "_dof"]), g[prefix + "_coord"],
+                        g[prefix + "_depth"], g[prefix + "_coeff"])
+
+
+def _api():
+    from tbslas_b200 import api
+    return api
+
+
+def adaptive_leaves(max_depth=5, min_depth=2):
+    def refine(lower, edge, d):
+        c = lower + 0.5 * edge[:, None]
+        r = np.sqrt(((c - np.array([0.55, 0.5, 0.45])) ** 2).sum(axis=1))
+        return np.abs(r - 0.3) < edge
+    return ftm.adaptive_leaves(refine, min_depth, max_depth)
+
+
+# ---------------------------------------------------------------- golden fixtures
+def test_gpu_kat_appendix_c(ctx):
+    api = _api()
+    g = golden("kat_depth1.npz")
+    t = ctx.tree(_tree(g))
+    f = api.NodeFieldFunctor(t)
+    for bc in (0, 1):
+        pos = g["pts"].copy()
+        v, leaf = f.eval_with_leaf(pos, bc)
+        assert np.array_equal(leaf, g["leaf_bc%d" % bc])
+        assert np.array_equal(v, g["val_bc%d" % bc])  # single-term sums: exact
+        assert np.array_equal(pos, g["pos_bc%d" % bc])  # wrapped in place like the reference
+
+
+def test_gpu_golden_eval_adaptive(ctx):
+    api = _api()
+    g = golden("eval_adaptive_q6.npz")
+    f = api.NodeFieldFunctor(ctx.tree(_tree(g)))
+    for bc in (0, 1):
+        pos = g["pts"].copy()
+        v, leaf = f.eval_with_leaf(pos, bc)
+        assert np.array_equal(leaf, g["leaf_bc%d" % bc])
+        assert np.array_equal(pos, g["pos_bc%d" % bc])
+        assert rel_err(v, g["val_bc%d" % bc]) < RTOL
+
+
+def test_gpu_golden_semilag(ctx):
+    api = _api()
+    g = golden("semilag_rotation_q5.npz")
+    vel = api.NodeFieldFunctor(ctx.tree(_tree(g, "vel")))
+    con = api.NodeFieldFunctor(ctx.tree(_tree(g, "con")))
+    dt, ts, nrk = float(g["dt"]), int(g["timestep"]), int(g["nrk"])
+    for bc in (0, 1):
+        x = api.ComputeTrajRK2(vel, g["pts"], ts * dt, ts * dt - dt, nrk, bc)
+        assert np.abs(x - g["traj_bc%d" % bc]).max() < RTOL
+        s = api.SolveSemilagRK2(vel, con, g["pts"], ts, dt, nrk, bc)
+        assert rel_err(s, g["semilag_bc%d" % bc]) < 1e-11  # value error + gradient * position error
+
+
+def test_gpu_golden_timevarying(ctx):
+    api = _api()
+    g = golden("timevarying_q4.npz")
+    trees = [ctx.tree(ftm.FlatTree(int(g["q"]), int(g["dof"]), g["coord"], g["depth"], g["coeff4"][i]))
+             for i in range(4)]
+    fset = api.FieldSetFunctor(trees, g["times"].tolist())
+    fext = api.FieldExtrapFunctor(trees[0], trees[1])
+    fcur = api.NodeFieldFunctor(trees[1])
+    for bc in (0, 1):
+        v = fset(g["pts"].copy(), time=float(g["tq"]), bc=bc)
+        assert rel_err(v, g["set4_bc%d" % bc]) < RTOL
+        e = fext(g["pts"].copy(), bc=bc)
+        assert rel_err(e, g["extrap_bc%d" % bc]) < RTOL
+        x = api.ComputeTrajRK2(fset, g["pts"], 0.1, 0.0, 1, bc)
+        assert np.abs(x - g["traj_set4_bc%d" % bc]).max() < RTOL
+        x = api.ComputeTrajRK2(fcur, g["pts"], 0.1, 0.0, 1, bc, extrap_fn=fext)
+        assert np.abs(x - g["traj_extrap_bc%d" % bc]).max() < RTOL
+
+
+def test_gpu_golden_cubic_grid(ctx):
+    g = golden("cubic_grid_n12.npz")
+    v = ctx.fast_interp(np.ascontiguousarray(g["grid"]), int(g["dof"]), int(g["n_reg"]), g["pts"])
+    assert np.array_equal(v, g["val"])  # un-fused, same order: bit-exact
+
+
+# ---------------------------------------------------------------- seeded parity vs oracle
+@pytest.mark.parametrize("q", list(range(1, 20)))
+def test_gpu_eval_every_degree(ctx, port, q):
+    api = _api()
+    coord, dd = ftm.uniform_leaves(2)
+    dof = 3 if q % 2 else 1
+    ft = ftm.random_tree(coord, dd, q, dof, seed=100 + q)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    rng = np.random.default_rng(q)
+    pts = rng.uniform(-0.02, 1.02, size=(6000 + 37 * q, 3))
+    for bc in (0, 1):
+        vo, lo, po = port.eval_tree(h, dof, pts, bc)
+        pos = pts.copy()
+        v, leaf = f.eval_with_leaf(pos, bc)
+        assert np.array_equal(leaf, lo)
+        assert np.array_equal(pos, po)
+        assert rel_err(v, vo) < RTOL
+
+
+@pytest.mark.parametrize("q,dof,bc", [(8, 3, 0), (14, 1, 1), (4, 2, 1), (14, 3, 0)])
+def test_gpu_eval_adaptive_tree(ctx, port, q, dof, bc):
+    api = _api()
+    coord, dd = adaptive_leaves()
+    ft = ftm.random_tree(coord, dd, q, dof, seed=q + dof)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    rng = np.random.default_rng(7)
+    pts = np.concatenate([rng.uniform(-0.1, 1.1, size=(60000, 3)),
+                          rng.integers(0, 65, size=(3000, 3)) / 64.0,      # leaf faces and corners
+                          0.3 + 0.01 * rng.standard_normal((20000, 3))])  # one crowded region
+    vo, lo, po = port.eval_tree(h, dof, pts, bc)
+    pos = pts.copy()
+    v, leaf = f.eval_with_leaf(pos, bc)
+    assert np.array_equal(leaf, lo)
+    assert np.array_equal(pos, po)
+    assert rel_err(v, vo) < RTOL
+
+
+def test_gpu_edge_cases(ctx, port):
+    api = _api()
+    coord, dd = ftm.uniform_leaves(1)
+    ft = ftm.random_tree(coord, dd, 5, 3, seed=3)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    # empty input
+    v, leaf = f.eval_with_leaf(np.zeros((0, 3)), 0)
+    assert v.shape == (0, 3) and leaf.shape == (0,)
+    # single point, ragged counts, everything in one leaf, everything outside
+    for pts in (np.array([[0.3, 0.6, 0.9]]),
+                np.random.default_rng(1).uniform(0, 1, size=(1000 + 13, 3)),
+                0.1 + 0.3 * np.random.default_rng(2).uniform(0, 1, size=(5000, 3)),
+                1.5 + np.random.default_rng(3).uniform(0, 1, size=(257, 3)),
+                -np.random.default_rng(4).uniform(0.1, 1, size=(100, 3))):
+        vo, lo, _ = port.eval_tree(h, 3, pts, 0)
+        v, leaf = f.eval_with_leaf(pts.copy(), 0)
+        assert np.array_equal(leaf, lo)
+        assert rel_err(v, vo) < RTOL or np.abs(vo).max() == 0 and np.abs(v).max() == 0
+    # NaN coordinates: no leaf arithmetic may trap; value is 0 like any out-of-domain point
+    v, leaf = f.eval_with_leaf(np.array([[np.nan, 0.5, 0.5], [0.25, 0.25, 0.25]]), 0)
+    assert leaf[1] == 0 and v[0].tolist() == [0, 0, 0]
+
+
+def test_gpu_partial_tree_null_leaf(ctx, port):
+    """A leaf list that does not start at the origin (one rank's shard): points before the
+    first leaf get leaf -1 and value 0 (the reference never evaluates them)."""
+    api = _api()
+    coord, dd = ftm.uniform_leaves(2)
+    ft = ftm.random_tree(coord, dd, 4, 1, seed=9).shard(20, 50)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    pts = np.random.default_rng(5).uniform(0, 1, size=(4000, 3))
+    vo, lo, _ = port.eval_tree(h, 1, pts, 0)
+    v, leaf = f.eval_with_leaf(pts.copy(), 0)
+    assert (lo == -1).any()
+    assert np.array_equal(leaf, lo)
+    assert rel_err(v, vo) < RTOL
+
+
+@pytest.mark.parametrize("bc", [0, 1])
+@pytest.mark.parametrize("nrk", [1, 3])
+def test_gpu_traj_and_semilag_vs_oracle(ctx, port, bc, nrk):
+    api = _api()
+    coord, dd = adaptive_leaves(4, 2)
+    tv = ftm.fit(coord, dd, 8, 3, lambda p: ftm.vel_rotation(p) + 0.05 * ftm.vel_taylor_green(p))
+    tc = ftm.fit(coord, dd, 8, 1, lambda p: ftm.gaussian(p, sigma=0.12))
+    vel, con = api.NodeFieldFunctor(ctx.tree(tv)), api.NodeFieldFunctor(ctx.tree(tc))
+    hv, hc = port.tree_create(tv), port.tree_create(tc)
+    pts = ftm.grid_points(coord, dd, 8)[::7].copy()  # a subset of the real arrival points
+    dt = 0.0628
+    xo = port.traj_rk2(hv, pts, 2 * dt, dt, nrk, bc)
+    x = api.ComputeTrajRK2(vel, pts, 2 * dt, dt, nrk, bc)
+    assert np.abs(x - xo).max() < RTOL
+    so = port.semilag_rk2(hv, hc, 1, pts, 2, dt, nrk, bc)
+    dep = np.empty_like(pts)
+    s = api.SolveSemilagRK2(vel, con, pts, 2, dt, nrk, bc, departure_points=dep)
+    assert np.abs(dep - xo).max() < RTOL
+    assert rel_err(s, so) < 1e-11
+
+
+def test_gpu_device_resident_buffers(ctx, port):
+    """Same results when the caller's buffers are device pointers (torch CUDA tensors)."""
+    import torch
+    api = _api()
+    coord, dd = ftm.uniform_leaves(3)
+    tv = ftm.fit(coord, dd, 6, 3, ftm.vel_rotation)
+    tc = ftm.random_tree(coord, dd, 6, 1, seed=4)
+    vel, con = api.NodeFieldFunctor(ctx.tree(tv)), api.NodeFieldFunctor(ctx.tree(tc))
+    pts = np.random.default_rng(11).uniform(0, 1, size=(50000, 3))
+    host = api.SolveSemilagRK2(vel, con, pts, 1, 0.05, 1, 1)
+    ctx.set_stream(torch.cuda.current_stream())
+    dpts = torch.from_numpy(pts).cuda()
+    dev = api.SolveSemilagRK2(vel, con, dpts, 1, 0.05, 1, 1)
+    torch.cuda.synchronize()
+    ctx.set_stream(None)
+    assert np.array_equal(dev.cpu().numpy(), host)
+    assert np.array_equal(dpts.cpu().numpy(), pts)  # arrival points are not modified
+
+
+def test_gpu_grid_points_bit_exact(ctx, port):
+    coord, dd = adaptive_leaves(4, 1)
+    for q in (3, 8, 14):
+        ft = ftm.random_tree(coord, dd, q, 1, seed=q)
+        t = ctx.tree(ft)
+        got = t.collect_grid_points()
+        h = port.tree_create(ft)
+        want = np.empty_like(got)
+        port.lib.orc_collect_grid_points(h, want.ctypes.data_as(
+            __import__("ctypes").POINTER(__import__("ctypes").c_double)))
+        assert np.array_equal(got, want)
+
+
+def test_gpu_cubic_grid_vs_oracle(ctx, port):
+    rng = np.random.default_rng(8)
+    for n_reg, dof in ((4, 1), (33, 3), (64, 1)):
+        grid = rng.standard_normal((dof, n_reg, n_reg, n_reg))
+        pts = rng.uniform(-0.02, 1.02, size=(40000, 3))
+        pts[:64] = rng.integers(0, n_reg, size=(64, 3)) / (n_reg - 1.0)
+        assert np.array_equal(ctx.fast_interp(grid, dof, n_reg, pts),
+                              port.fast_interp(grid, dof, n_reg, pts))
+
+
+# ---------------------------------------------------------------- size-independent properties
+def test_gpu_properties_at_config1_size(ctx):
+    """BASELINE config 1 size (uniform depth 4, q = 8, N = 2 985 984 arrival points)."""
+    api = _api()
+    coord, dd = ftm.uniform_leaves(4)
+    q = 8
+    pts = ftm.grid_points(coord, dd, q)
+    assert pts.shape[0] == 2985984
+    # (1) polynomial reproduction: a degree-<=q polynomial field is exact at every point
+    def poly(p):
+        x, y, z = p[:, 0], p[:, 1], p[:, 2]
+        return np.stack([1 + x - 2 * y * z, x * x * y - z ** 3, 0.5 + x ** 4 * y ** 2 * z ** 2], axis=1)
+    tp = ftm.fit(coord, dd, q, 3, poly)
+    f = api.NodeFieldFunctor(ctx.tree(tp))
+    rng = np.random.default_rng(0)
+    moved = pts + 0.01 * rng.standard_normal(pts.shape)
+    v, leaf = f.eval_with_leaf(moved, 1)  # periodic: wraps in place
+    assert np.abs(v - poly(moved)).max() < 1e-11
+    # (2) leaf ids are exactly floor(coordinate * 16) in Morton order
+    a = np.floor(moved * 16).astype(np.uint64)
+    order = np.argsort(ftm.anchor_key(a[:, 0] << np.uint64(11), a[:, 1] << np.uint64(11),
+                                      a[:, 2] << np.uint64(11)), kind="stable")
+    lut = {}
+    keys = ftm.FlatTree(q, 3, coord, dd, tp.coeff).keys()
+    pk = ftm.anchor_key(a[:, 0] << np.uint64(11), a[:, 1] << np.uint64(11), a[:, 2] << np.uint64(11))
+    assert np.array_equal(leaf, np.searchsorted(keys, pk, side="right") - 1)
+    # (3) linearity: eval(a*A + b*B) == a*eval(A) + b*eval(B) to rounding
+    A = ftm.random_tree(coord, dd, q, 1, seed=1)
+    B = ftm.random_tree(coord, dd, q, 1, seed=2)
+    AB = ftm.FlatTree(q, 1, coord, dd, 0.75 * A.coeff - 1.25 * B.coeff)
+    va = api.NodeFieldFunctor(ctx.tree(A))(moved, bc=1)
+    vb = api.NodeFieldFunctor(ctx.tree(B))(moved, bc=1)
+    vab = api.NodeFieldFunctor(ctx.tree(AB))(moved, bc=1)
+    assert np.abs(vab - (0.75 * va - 1.25 * vb)).max() < 1e-12 * max(1.0, np.abs(va).max())
+    # (4) semi-Lagrangian round trip: forward then backward rotation returns to the start
+    tv = ftm.fit(coord, dd, q, 3, ftm.vel_rotation)
+    vel = api.NodeFieldFunctor(ctx.tree(tv))
+    inner = pts[np.linalg.norm(pts[:, :2] - 0.5, axis=1) < 0.4]
+    fwd = api.ComputeTrajRK2(vel, inner, 0.0, 0.05, 4, 0)
+    back = api.ComputeTrajRK2(vel, fwd, 0.05, 0.0, 4, 0)
+    assert np.abs(back - inner).max() < 1e-7  # O(dt^3) scheme, reversible to truncation error
