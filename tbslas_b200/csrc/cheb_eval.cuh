@@ -96,10 +96,94 @@ __device__ __forceinline__ void cheb_basis(double xi, double (&T)[Q + 1]) {
   for (int i = 2; i <= Q; i++) T[i] = __dsub_rn(__dmul_rn(x2, T[i - 1]), T[i - 2]);
 }
 
-template <int Q, int PPT, int EPI>
+// ---- compile-time expansion of the triangular contraction ------------------------
+// The loops of pvfmm::vec_eval (tree_functor.h:38-77) are expanded by template recursion
+// (not `#pragma unroll`, which nvcc abandons for bodies this large): every coefficient
+// offset, basis index and trip count below is a compile-time constant, so T_k(x), T_j(y)
+// stay in registers and coefficient reads are LDS.128 at immediate offsets.
+//
+// Rows (i,j) and (i,j+1) are contracted together so a thread always has 2*PPT independent
+// DFMA chains in flight (DFMA latency 8 cycles, issue interval 2).
+template <int Q, int PPT, bool PYS, bool PAIR, int I, int J, int CI>
+struct RowPair {
+  static constexpr int D = Q + 1;
+  static constexpr int N0 = D - I - J;          // terms in row J
+  static constexpr bool TWO = PAIR && (J + 1 < D - I);  // row J+1 exists (N0-1 >= 1 terms)
+  static constexpr int NEXT = CI + N0 + (TWO ? N0 - 1 : 0);
+  static __device__ __forceinline__ double coef(const double2 *C2, int i) {
+    return (i & 1) ? C2[i >> 1].y : C2[i >> 1].x;
+  }
+  static __device__ __forceinline__ void run(const double2 *__restrict__ C2,
+                                             const double (&px)[PPT][D],
+                                             const double (&py)[PYS ? 1 : PPT][D],
+                                             const double *s_py, double (&v)[PPT]) {
+    double w0[PPT], w1[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) w0[s] = w1[s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N0; k++) {
+      const double c0 = coef(C2, CI + k);
+#pragma unroll
+      for (int s = 0; s < PPT; s++) w0[s] = fma(px[s][k], c0, w0[s]);
+      if (TWO && k < N0 - 1) {
+        const double c1 = coef(C2, CI + N0 + k);
+#pragma unroll
+        for (int s = 0; s < PPT; s++) w1[s] = fma(px[s][k], c1, w1[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+      v[s] = fma(PYS ? s_py[(J * PPT + s) * kEvalThreads] : py[PYS ? 0 : s][J], w0[s], v[s]);
+      if (TWO)
+        v[s] = fma(PYS ? s_py[((J + 1) * PPT + s) * kEvalThreads] : py[PYS ? 0 : s][TWO ? J + 1 : J],
+                   w1[s], v[s]);
+    }
+    if constexpr (J + (PAIR ? 2 : 1) < D - I)
+      RowPair<Q, PPT, PYS, PAIR, I, J + (PAIR ? 2 : 1), NEXT>::run(C2, px, py, s_py, v);
+  }
+};
+
+template <int Q, int PPT, bool PYS, bool PAIR, int I, int CI>
+struct ZLevel {
+  static constexpr int D = Q + 1;
+  static __device__ __forceinline__ void run(const double2 *__restrict__ C2,
+                                             const double (&px)[PPT][D],
+                                             const double (&py)[PYS ? 1 : PPT][D],
+                                             const double *s_py, const double (&zc)[PPT],
+                                             const double (&z0)[PPT], double (&tz0)[PPT],
+                                             double (&tz1)[PPT], double (&u)[PPT]) {
+    double pz[PPT], v[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {  // T_I(z) by its recurrence (mul, sub: bit-exact basis)
+      if (I == 0)
+        pz[s] = z0[s];
+      else if (I == 1)
+        pz[s] = zc[s];
+      else
+        pz[s] = __dsub_rn(__dmul_rn(2.0 * zc[s], tz1[s]), tz0[s]);
+      tz0[s] = (I == 0) ? 0.0 : tz1[s];
+      tz1[s] = pz[s];
+      v[s] = 0.0;
+    }
+    RowPair<Q, PPT, PYS, PAIR, I, 0, CI>::run(C2, px, py, s_py, v);
+#pragma unroll
+    for (int s = 0; s < PPT; s++) u[s] = fma(pz[s], v[s], u[s]);
+    if constexpr (I + 1 < D)
+      ZLevel<Q, PPT, PYS, PAIR, I + 1, CI + (D - I) * (D - I + 1) / 2>::run(C2, px, py, s_py, zc, z0, tz0,
+                                                                      tz1, u);
+  }
+};
+
+// PYS: keep T_j(y) in shared memory ([j][point slot][thread], conflict free) instead of
+// registers -- frees 2*(Q+1)*PPT registers so high degrees can run more points per thread.
+// NB: batches of 32*PPT points a warp works through for the same leaf; the coordinates of
+// batch b+1 are fetched while batch b is being contracted (hides the gather latency that
+// two resident CTAs per SM cannot).
+template <int Q, int PPT, int EPI, bool PYS, int NB, bool PAIR>
 __global__ void __launch_bounds__(kEvalThreads)
 cheb_eval_kernel(const EvalParams p) {
   constexpr int D = Q + 1;
+  constexpr int NW = kEvalThreads / 32;
   extern __shared__ __align__(128) double s_coef[];
   __shared__ __align__(8) uint64_t s_bar;
 
@@ -109,7 +193,7 @@ cheb_eval_kernel(const EvalParams p) {
   const int leaf = tile.x;
   const unsigned slot0 = (unsigned)tile.y;
   const unsigned bin_end = __ldg(p.bin_start + leaf + 1);
-  const unsigned cnt = min((unsigned)(kEvalThreads * PPT), bin_end - slot0);
+  const unsigned cnt = min((unsigned)(kEvalThreads * PPT * NB), bin_end - slot0);
 
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
@@ -120,90 +204,99 @@ cheb_eval_kernel(const EvalParams p) {
   }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned wbase = warp * 32 * PPT;
-  if (wbase >= cnt) return;  // whole warp has no points (no barrier follows)
+  unsigned wbase = warp * 32 * PPT;  // batch t = b*NW + warp starts at slot t*32*PPT
+  if (wbase >= cnt) return;          // whole warp has no points (no barrier follows)
 
   const double4 g = p.geom[leaf];
-  unsigned idx[PPT];
-  bool ok[PPT];
-  double px[PPT][D], py[PPT][D], zc[PPT], z0[PPT];
+  double *s_py = s_coef + p.stride + threadIdx.x;  // [(j*PPT + s)*kEvalThreads]
+  const uint32_t *perm0 = p.perm + slot0;
+
+  // coordinates of the first batch
+  unsigned idx_n[PPT];
+  double xn[PPT][3];
 #pragma unroll
   for (int s = 0; s < PPT; s++) {
     const unsigned slot = wbase + s * 32 + lane;
-    ok[s] = slot < cnt;
-    idx[s] = __ldg(p.perm + slot0 + (ok[s] ? slot : 0u));
-    const double *x = p.pos + 3 * (size_t)idx[s];
-    // xi = (x - c) * 2 * 2^depth - 1, left to right (tree_functor.h:288-293); the
-    // power-of-two scalings are exact, so one multiply by 2*2^depth is the same value.
-    const double xi = __dadd_rn(__dmul_rn(__dsub_rn(x[0], g.x), g.w), -1.0);
-    const double yi = __dadd_rn(__dmul_rn(__dsub_rn(x[1], g.y), g.w), -1.0);
-    const double zi = __dadd_rn(__dmul_rn(__dsub_rn(x[2], g.z), g.w), -1.0);
-    cheb_basis<Q>(xi, px[s]);
-    cheb_basis<Q>(yi, py[s]);
-    const bool inz = fabs(zi) <= 1.0;
-    zc[s] = inz ? zi : 0.0;
-    z0[s] = inz ? 1.0 : 0.0;
+    idx_n[s] = __ldg(perm0 + (slot < cnt ? slot : wbase));
+    const double *x = p.pos + 3 * (size_t)idx_n[s];
+    xn[s][0] = x[0];
+    xn[s][1] = x[1];
+    xn[s][2] = x[2];
   }
-
-  mbar_wait(&s_bar, 0);
+  bool waited = false;
 
 #pragma unroll 1
-  for (int l = 0; l < p.dof; l++) {
-    const double2 *C2 = reinterpret_cast<const double2 *>(s_coef + l * p.ncoef_pad);
-    double u[PPT], tz0[PPT], tz1[PPT];
-#pragma unroll
-    for (int s = 0; s < PPT; s++) u[s] = 0.0;
-    double2 cc = make_double2(0.0, 0.0);
-    int ci = 0;  // compile-time after unrolling
-#pragma unroll
-    for (int i = 0; i < D; i++) {
-      double pz[PPT], v[PPT];
-#pragma unroll
-      for (int s = 0; s < PPT; s++) {
-        if (i == 0)
-          pz[s] = z0[s];
-        else if (i == 1)
-          pz[s] = zc[s];
-        else
-          pz[s] = __dsub_rn(__dmul_rn(2.0 * zc[s], tz1[s]), tz0[s]);
-        tz0[s] = (i == 0) ? 0.0 : tz1[s];
-        tz1[s] = pz[s];
-        v[s] = 0.0;
-      }
-#pragma unroll
-      for (int j = 0; j < D - i; j++) {
-        double w[PPT];
-#pragma unroll
-        for (int s = 0; s < PPT; s++) w[s] = 0.0;
-#pragma unroll
-        for (int k = 0; k < D - i - j; k++) {
-          if ((ci & 1) == 0) cc = C2[ci >> 1];
-          const double c = (ci & 1) ? cc.y : cc.x;
-          ci++;
-#pragma unroll
-          for (int s = 0; s < PPT; s++) w[s] = fma(px[s][k], c, w[s]);
-        }
-#pragma unroll
-        for (int s = 0; s < PPT; s++) v[s] = fma(py[s][j], w[s], v[s]);
-      }
-#pragma unroll
-      for (int s = 0; s < PPT; s++) u[s] = fma(pz[s], v[s], u[s]);
-    }
+  for (int b = 0; b < NB; b++) {
+    unsigned idx[PPT];
+    bool ok[PPT];
+    double px[PPT][D], py[PYS ? 1 : PPT][D], zc[PPT], z0[PPT];
 #pragma unroll
     for (int s = 0; s < PPT; s++) {
-      if (ok[s]) {
-        if (EPI == EPI_STORE) {
-          p.out[(size_t)idx[s] * p.dof + l] = u[s];
-        } else {  // x' = x0 + alpha * v, multiply then add as traj.inc:36,42
-          const size_t o = 3 * (size_t)idx[s] + l;
-          p.out[o] = __dadd_rn(p.base[o], __dmul_rn(p.alpha, u[s]));
+      idx[s] = idx_n[s];
+      ok[s] = wbase + s * 32 + lane < cnt;
+      // xi = (x - c) * 2 * 2^depth - 1, left to right (tree_functor.h:288-293); the
+      // power-of-two scalings are exact, so one multiply by 2*2^depth is the same value.
+      const double xi = __dadd_rn(__dmul_rn(__dsub_rn(xn[s][0], g.x), g.w), -1.0);
+      const double yi = __dadd_rn(__dmul_rn(__dsub_rn(xn[s][1], g.y), g.w), -1.0);
+      const double zi = __dadd_rn(__dmul_rn(__dsub_rn(xn[s][2], g.z), g.w), -1.0);
+      cheb_basis<Q>(xi, px[s]);
+      if (PYS) {
+        cheb_basis<Q>(yi, py[0]);
+#pragma unroll
+        for (int j = 0; j < D; j++) s_py[(j * PPT + s) * kEvalThreads] = py[0][j];
+      } else {
+        cheb_basis<Q>(yi, py[s]);
+      }
+      const bool inz = fabs(zi) <= 1.0;
+      zc[s] = inz ? zi : 0.0;
+      z0[s] = inz ? 1.0 : 0.0;
+    }
+    // prefetch the next batch of this warp (consumed after the contraction below)
+    const unsigned wnext = wbase + NW * 32 * PPT;
+    const bool more = (b + 1 < NB) && (wnext < cnt);
+    if (more) {
+#pragma unroll
+      for (int s = 0; s < PPT; s++) {
+        const unsigned slot = wnext + s * 32 + lane;
+        idx_n[s] = __ldg(perm0 + (slot < cnt ? slot : wnext));
+        const double *x = p.pos + 3 * (size_t)idx_n[s];
+        xn[s][0] = x[0];
+        xn[s][1] = x[1];
+        xn[s][2] = x[2];
+      }
+    }
+    if (!waited) {
+      mbar_wait(&s_bar, 0);
+      waited = true;
+    }
+
+#pragma unroll 1
+    for (int l = 0; l < p.dof; l++) {
+      const double2 *C2 = reinterpret_cast<const double2 *>(s_coef + l * p.ncoef_pad);
+      double u[PPT], tz0[PPT], tz1[PPT];
+#pragma unroll
+      for (int s = 0; s < PPT; s++) u[s] = tz0[s] = tz1[s] = 0.0;
+      ZLevel<Q, PPT, PYS, PAIR, 0, 0>::run(C2, px, py, s_py, zc, z0, tz0, tz1, u);
+#pragma unroll
+      for (int s = 0; s < PPT; s++) {
+        if (ok[s]) {
+          if (EPI == EPI_STORE) {
+            p.out[(size_t)idx[s] * p.dof + l] = u[s];
+          } else {  // x' = x0 + alpha * v, multiply then add as traj.inc:36,42
+            const size_t o = 3 * (size_t)idx[s] + l;
+            p.out[o] = __dadd_rn(p.base[o], __dmul_rn(p.alpha, u[s]));
+          }
         }
       }
     }
+    if (!more) break;
+    wbase = wnext;
   }
 }
 
-template <int Q, int PPT>
+constexpr int kEvalBatches = 1;  // batches of 32*PPT points per warp and tile (measured: 1 is best)
+
+template <int Q, int PPT, bool PYS = false, int NB = kEvalBatches, bool PAIR = false>
 int launch_cheb_eval_q(tbslas_ctx *ctx, const EvalArgs &a) {
   const tbslas_tree *t = a.tree;
   EvalParams p;
@@ -221,16 +314,17 @@ int launch_cheb_eval_q(tbslas_ctx *ctx, const EvalArgs &a) {
   p.out = a.out;
   p.base = a.base;
   p.alpha = a.alpha;
-  const size_t smem = t->stride * sizeof(double);
+  const size_t smem =
+      (t->stride + (PYS ? (size_t)(Q + 1) * PPT * kEvalThreads : 0)) * sizeof(double);
   const unsigned grid = (unsigned)a.max_tiles;
   if (grid == 0) return TBSLAS_OK;
   if (a.epilogue == EPI_STORE) {
-    auto k = cheb_eval_kernel<Q, PPT, EPI_STORE>;
+    auto k = cheb_eval_kernel<Q, PPT, EPI_STORE, PYS, NB, PAIR>;
     if (smem > 48 * 1024)
       TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kEvalThreads, smem, ctx->stream>>>(p);
   } else {
-    auto k = cheb_eval_kernel<Q, PPT, EPI_AXPY>;
+    auto k = cheb_eval_kernel<Q, PPT, EPI_AXPY, PYS, NB, PAIR>;
     if (smem > 48 * 1024)
       TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kEvalThreads, smem, ctx->stream>>>(p);

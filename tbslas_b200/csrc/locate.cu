@@ -50,108 +50,184 @@ __device__ __forceinline__ int lane_count_le(const uint64_t *__restrict__ keys, 
   return lo;
 }
 
+// One CTA walks kLocItems*kLocateThreads consecutive points.  Histogram updates go to
+// a small shared-memory table (bin -> count) first, so the global bin counters see one
+// atomic per (CTA, distinct bin) instead of one per warp: departure points of one source
+// leaf land in a handful of leaves, and thousands of same-address L2 atomics serialise.
+constexpr int kLocItems = 8;
+constexpr int kLocTable = 64;  // distinct bins a CTA can aggregate; overflow -> direct atomics
+
+__device__ __forceinline__ int table_slot(int *s_bin, int bin) {
+  unsigned h = ((unsigned)bin * 2654435761u) >> 26;  // log2(kLocTable) = 6 bits
+  for (int probe = 0; probe < kLocTable; probe++) {
+    const int old = atomicCAS(s_bin + h, -1, bin);
+    if (old == -1 || old == bin) return (int)h;
+    h = (h + 1) & (kLocTable - 1);
+  }
+  return -1;
+}
+
+// Bins: 0..n_leaf-1 leaves, n_leaf = "no leaf" (evaluates to 0), n_leaf+2+r = points owned
+// by rank r (multi-rank only; count[] holds the send counts right after the leaf bins).
 template <bool MULTI>
 __global__ void __launch_bounds__(kLocateThreads)
 locate_kernel(const uint64_t *__restrict__ keys, int n_leaf, int periodic, double *__restrict__ pos,
               size_t n, int32_t *__restrict__ leaf_out, uint32_t *__restrict__ rank_out,
               uint32_t *__restrict__ count, const uint64_t *__restrict__ splitters, int nranks,
-              int myrank, uint32_t *__restrict__ send_count) {
-  const size_t i = (size_t)blockIdx.x * kLocateThreads + threadIdx.x;
+              int myrank) {
+  __shared__ int s_bin[kLocTable];
+  __shared__ unsigned s_cnt[kLocTable];
+  __shared__ unsigned s_base[kLocTable];
+  if (threadIdx.x < kLocTable) {
+    s_bin[threadIdx.x] = -1;
+    s_cnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const bool valid = i < n;
-  uint64_t key = 0;
-  if (valid) {
-    double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
-    if (periodic) {
-      const double x0 = x, y0 = y, z0 = z;
-      x = wrap_periodic(x);
-      y = wrap_periodic(y);
-      z = wrap_periodic(z);
-      if (x != x0) pos[3 * i] = x;  // the reference rewrites the caller's buffer
-      if (y != y0) pos[3 * i + 1] = y;
-      if (z != z0) pos[3 * i + 2] = z;
-    }
-    key = point_key(x, y, z, periodic);
-  }
-  int my_leaf = 0;
-  uint32_t my_rank = 0;
-  bool todo = valid;
+  const unsigned lt = (1u << lane) - 1;
+  const size_t chunk0 = (size_t)blockIdx.x * (kLocateThreads * kLocItems);
+  int my_bin[kLocItems], my_slot[kLocItems];
+  uint32_t my_rank[kLocItems];
 
-  if (MULTI && valid) {
-    // owner = last rank whose first-leaf key is <= key (rank 0 below the first)
-    uint64_t lo_key = __ldg(splitters + myrank);
-    bool mine = key >= lo_key || myrank == 0;
-    if (myrank + 1 < nranks) mine = mine && key < __ldg(splitters + myrank + 1);
-    if (!mine) {
-      int owner = 0;
-      for (int r = 1; r < nranks; r++)
-        if (__ldg(splitters + r) <= key) owner = r;
-      todo = false;
-      const unsigned peers = __match_any_sync(__activemask(), owner);
-      const int leader = __ffs(peers) - 1;
+  auto claim = [&](int bin, unsigned m, int leader, int &slot, uint32_t &base) {
+    // one table (or, on overflow, global) update for the lanes in m, all in `bin`
+    if (lane == leader) {
+      slot = table_slot(s_bin, bin);
+      base = (slot >= 0) ? atomicAdd(s_cnt + slot, (unsigned)__popc(m))
+                         : atomicAdd(count + bin, (unsigned)__popc(m));
+    }
+  };
+
+#pragma unroll 1
+  for (int it = 0; it < kLocItems; it++) {
+    const size_t i = chunk0 + (size_t)it * kLocateThreads + threadIdx.x;
+    const bool valid = i < n;
+    uint64_t key = 0;
+    if (valid) {
+      double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+      if (periodic) {
+        const double x0 = x, y0 = y, z0 = z;
+        x = wrap_periodic(x);
+        y = wrap_periodic(y);
+        z = wrap_periodic(z);
+        if (x != x0) pos[3 * i] = x;  // the reference rewrites the caller's buffer
+        if (y != y0) pos[3 * i + 1] = y;
+        if (z != z0) pos[3 * i + 2] = z;
+      }
+      key = point_key(x, y, z, periodic);
+    }
+    int bin = 0, slot = -1;
+    uint32_t rank = 0;
+    bool todo = valid;
+
+    if (MULTI) {
+      // owner = last rank whose first-leaf key is <= key (rank 0 below the first)
+      bool mine = true;
+      int owner = myrank;
+      if (valid) {
+        mine = (key >= __ldg(splitters + myrank)) || myrank == 0;
+        if (myrank + 1 < nranks) mine = mine && key < __ldg(splitters + myrank + 1);
+        if (!mine) {
+          owner = 0;
+          for (int r = 1; r < nranks; r++)
+            if (__ldg(splitters + r) <= key) owner = r;
+        }
+      }
+      unsigned out = __ballot_sync(0xffffffffu, valid && !mine);
+      while (out) {  // one aggregated update per destination rank present in the warp
+        const int leader = __ffs(out) - 1;
+        const int o = __shfl_sync(0xffffffffu, owner, leader);
+        const unsigned m = __ballot_sync(0xffffffffu, ((out >> lane) & 1u) && owner == o);
+        int sl = -1;
+        uint32_t base = 0;
+        claim(n_leaf + 2 + o, m, leader, sl, base);
+        sl = __shfl_sync(0xffffffffu, sl, leader);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if ((m >> lane) & 1u) {
+          bin = n_leaf + 2 + o;
+          slot = sl;
+          rank = base + __popc(m & lt);
+          todo = false;
+        }
+        out &= ~m;
+      }
+    }
+
+    // Warp-cooperative phase: departure points are spatially coherent, so most lanes of
+    // a warp share the leaf of the first unresolved lane.
+    unsigned pending = __ballot_sync(0xffffffffu, todo);
+    for (int c = 0; c < kCoopIters && pending; c++) {
+      const int leader = __ffs(pending) - 1;
+      const uint64_t lk = __shfl_sync(0xffffffffu, key, leader);
+      const int j = warp_count_le(keys, n_leaf, lk, lane) - 1;  // warp-uniform
+      const uint64_t klo = (j >= 0) ? __ldg(keys + j) : 0ull;
+      const bool last = (j + 1 >= n_leaf);
+      const uint64_t khi = last ? ~0ull : __ldg(keys + j + 1);
+      const bool hit = ((pending >> lane) & 1u) && key >= klo && (last || key < khi);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      const int b = (j >= 0) ? j : n_leaf;
+      int sl = -1;
       uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(send_count + owner, (uint32_t)__popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      my_rank = base + __popc(peers & ((1u << lane) - 1));
-      my_leaf = -2 - owner;
+      claim(b, m, leader, sl, base);
+      sl = __shfl_sync(0xffffffffu, sl, leader);
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (hit) {
+        bin = b;
+        slot = sl;
+        rank = base + __popc(m & lt);
+      }
+      pending &= ~m;
+      if (__popc(m) < 4) break;  // incoherent input: stop paying for warp-wide searches
     }
+    if ((pending >> lane) & 1u) {  // per-lane fallback, updates aggregated per leaf
+      const int j = lane_count_le(keys, n_leaf, key) - 1;
+      bin = (j >= 0) ? j : n_leaf;
+      const unsigned peers = __match_any_sync(pending, bin);
+      const int leader = __ffs(peers) - 1;
+      int sl = -1;
+      uint32_t base = 0;
+      claim(bin, peers, leader, sl, base);
+      slot = __shfl_sync(peers, sl, leader);
+      rank = __shfl_sync(peers, base, leader) + __popc(peers & lt);
+    }
+    my_bin[it] = valid ? bin : -1;
+    my_slot[it] = slot;
+    my_rank[it] = rank;
   }
 
-  // Warp-cooperative phase: departure points are spatially coherent, so most lanes of
-  // a warp share the leaf of the first unresolved lane.
-  unsigned pending = __ballot_sync(0xffffffffu, todo);
-  for (int it = 0; it < kCoopIters && pending; it++) {
-    const int leader = __ffs(pending) - 1;
-    const uint64_t lk = __shfl_sync(0xffffffffu, key, leader);
-    const int j = warp_count_le(keys, n_leaf, lk, lane) - 1;  // warp-uniform
-    const uint64_t klo = (j >= 0) ? __ldg(keys + j) : 0ull;
-    const bool last = (j + 1 >= n_leaf);
-    const uint64_t khi = last ? ~0ull : __ldg(keys + j + 1);
-    const bool hit = ((pending >> lane) & 1u) && key >= klo && (last || key < khi);
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    const int bin = (j >= 0) ? j : n_leaf;  // bin n_leaf = "no leaf" (evaluates to 0)
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(count + bin, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (hit) {
-      my_leaf = bin;
-      my_rank = base + __popc(m & ((1u << lane) - 1));
-    }
-    pending &= ~m;
-    if (__popc(m) < 4) break;  // incoherent input: stop paying for warp-wide searches
-  }
-  if ((pending >> lane) & 1u) {  // per-lane fallback, atomics aggregated per leaf
-    const int j = lane_count_le(keys, n_leaf, key) - 1;
-    const int bin = (j >= 0) ? j : n_leaf;
-    const unsigned peers = __match_any_sync(pending, bin);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(count + bin, (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    my_leaf = bin;
-    my_rank = base + __popc(peers & ((1u << lane) - 1));
-  }
-  if (valid) {
-    leaf_out[i] = my_leaf;
-    rank_out[i] = my_rank;
+  __syncthreads();
+  if (threadIdx.x < kLocTable && s_bin[threadIdx.x] >= 0)
+    s_base[threadIdx.x] = atomicAdd(count + s_bin[threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kLocItems; it++) {
+    if (my_bin[it] < 0) continue;
+    const size_t i = chunk0 + (size_t)it * kLocateThreads + threadIdx.x;
+    const int b = my_bin[it];
+    leaf_out[i] = (b <= n_leaf) ? b : -2 - (b - n_leaf - 2);
+    rank_out[i] = my_rank[it] + (my_slot[it] >= 0 ? s_base[my_slot[it]] : 0u);
   }
 }
 
 int launch_locate(tbslas_ctx *ctx, const LocateArgs &a) {
   const tbslas_tree *t = a.tree;
   StageScope sc(ctx, ST_LOCATE, (double)a.n, 1);
-  TB_CUDA(ctx, cudaMemsetAsync(a.count, 0, sizeof(uint32_t) * (t->n_leaf + 2), ctx->stream));
+  const bool multi = ctx->nranks > 1 && a.send_count;
+  TB_CUDA(ctx, cudaMemsetAsync(a.count, 0,
+                               sizeof(uint32_t) * (t->n_leaf + 2 + (multi ? ctx->nranks : 0)),
+                               ctx->stream));
   if (a.n == 0) return TBSLAS_OK;
-  const unsigned grid = (unsigned)((a.n + kLocateThreads - 1) / kLocateThreads);
-  if (ctx->nranks > 1 && a.send_count) {
-    TB_CUDA(ctx, cudaMemsetAsync(a.send_count, 0, sizeof(uint32_t) * ctx->nranks, ctx->stream));
+  const size_t per_cta = (size_t)kLocateThreads * kLocItems;
+  const unsigned grid = (unsigned)((a.n + per_cta - 1) / per_cta);
+  if (multi) {
+    if (a.send_count != a.count + t->n_leaf + 2)
+      return fail(ctx, TBSLAS_ERR_INVALID, "send counts must follow the leaf bins");
     locate_kernel<true><<<grid, kLocateThreads, 0, ctx->stream>>>(
         t->d_key, (int)t->n_leaf, a.periodic, a.pos, a.n, a.leaf, a.rank, a.count, t->d_splitters,
-        ctx->nranks, ctx->rank, a.send_count);
+        ctx->nranks, ctx->rank);
   } else {
     locate_kernel<false><<<grid, kLocateThreads, 0, ctx->stream>>>(
-        t->d_key, (int)t->n_leaf, a.periodic, a.pos, a.n, a.leaf, a.rank, a.count, nullptr, 1, 0,
-        nullptr);
+        t->d_key, (int)t->n_leaf, a.periodic, a.pos, a.n, a.leaf, a.rank, a.count, nullptr, 1, 0);
   }
   TB_CUDA(ctx, cudaGetLastError());
   return TBSLAS_OK;
@@ -166,8 +242,7 @@ constexpr int kScanItems = 4;
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_bins_kernel(const uint32_t *__restrict__ count, int n_bins, int tile_pts,
-                 uint32_t *__restrict__ bin_start, uint32_t *__restrict__ tile_start,
-                 int2 *__restrict__ tile_map, unsigned max_tiles) {
+                 uint32_t *__restrict__ bin_start, uint32_t *__restrict__ tile_start) {
   __shared__ unsigned long long warp_tot[32];
   __shared__ unsigned long long carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -211,9 +286,6 @@ scan_bins_kernel(const uint32_t *__restrict__ count, int n_bins, int tile_pts,
         const unsigned ps = (unsigned)(run & 0xffffffffu), ts = (unsigned)(run >> 32);
         bin_start[j] = ps;
         tile_start[j] = ts;
-        const unsigned nt = (unsigned)(v[k] >> 32);
-        for (unsigned c = 0; c < nt; c++)
-          if (ts + c < max_tiles) tile_map[ts + c] = make_int2(j, (int)(ps + c * tile_pts));
       }
       run += v[k];
     }
@@ -227,6 +299,24 @@ scan_bins_kernel(const uint32_t *__restrict__ count, int n_bins, int tile_pts,
   }
 }
 
+// tile t -> (leaf, first slot): every tile finds its leaf by binary search in tile_start
+__global__ void tile_map_kernel(const uint32_t *__restrict__ bin_start,
+                                const uint32_t *__restrict__ tile_start, int n_bins, int tile_pts,
+                                int2 *__restrict__ tile_map, unsigned max_tiles) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned n_tiles = min(__ldg(tile_start + n_bins), max_tiles);
+  if (t >= n_tiles) return;
+  int lo = 0, hi = n_bins;  // last j with tile_start[j] <= t (empty bins share a start: take the last)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(tile_start + mid) <= t)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  tile_map[t] = make_int2(lo, (int)(__ldg(bin_start + lo) + (t - __ldg(tile_start + lo)) * tile_pts));
+}
+
 __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint32_t *__restrict__ rank,
                                     const uint32_t *__restrict__ bin_start, size_t n,
                                     uint32_t *__restrict__ perm) {
@@ -238,11 +328,13 @@ __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint
 }
 
 int launch_bin(tbslas_ctx *ctx, const BinArgs &a) {
-  StageScope sc(ctx, ST_BIN, (double)a.n, 2);
+  StageScope sc(ctx, ST_BIN, (double)a.n, 3);
   const int n_bins = (int)a.n_leaf + 1;  // + null leaf
   scan_bins_kernel<<<1, kScanThreads, 0, ctx->stream>>>(a.count, n_bins, a.tile_pts, a.bin_start,
-                                                        a.tile_start, a.tile_map,
-                                                        (unsigned)a.max_tiles);
+                                                        a.tile_start);
+  TB_CUDA(ctx, cudaGetLastError());
+  tile_map_kernel<<<(unsigned)((a.max_tiles + 255) / 256), 256, 0, ctx->stream>>>(
+      a.bin_start, a.tile_start, n_bins, a.tile_pts, a.tile_map, (unsigned)a.max_tiles);
   TB_CUDA(ctx, cudaGetLastError());
   if (a.n) {
     const unsigned grid = (unsigned)((a.n + 255) / 256);
