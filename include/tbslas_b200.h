@@ -91,14 +91,19 @@ const char *tbslas_b200_version(void);
 int tbslas_b200_comm_unique_id(void *id128);
 int tbslas_b200_comm_init(tbslas_ctx *ctx, int nranks, int rank, const void *id128);
 int tbslas_b200_comm_rank(tbslas_ctx *ctx, int *rank, int *nranks);
+/* Outsider points this rank sent to / received from other ranks during the most recent
+ * tree evaluation (the cnt_outside of tree_functor.h:513-517 and its mirror image). */
+int tbslas_b200_comm_last_exchange(tbslas_ctx *ctx, size_t *sent, size_t *received);
 
 /* ---- trees -------------------------------------------------------------- */
 /* Replaces: the leaf walk at tree_functor.h:417-427 (GetNodeList filtered by
  * IsLeaf && !IsGhost) and the per-leaf reads of Coord/Depth/ChebData
  * (:249-266,:283-284).  Leaves must be in Morton (PVFMM preorder) order.  In a
  * multi-rank context every rank passes ITS OWN contiguous Morton range (what an MPI
- * rank of the reference owns); the first-leaf keys are all-gathered here, replacing
- * the per-call MPI_Allgather at tree_functor.h:433-437.
+ * rank of the reference owns; a rank may pass n_leaf = 0); the first-leaf keys are
+ * all-gathered here (a collective call: every rank must enter), replacing the per-call
+ * MPI_Allgather at tree_functor.h:433-437.  Every evaluation on such a tree is then
+ * collective as well, exactly like tbslas::EvalTree.
  *   coord  [n_leaf][3]   depth [n_leaf]   coeff [n_leaf][dof][Ncoef],
  *   Ncoef = (q+1)(q+2)(q+3)/6 in the reference's packed order (:256-266). */
 int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf,

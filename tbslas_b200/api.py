@@ -107,6 +107,12 @@ class Context:
         buf = (C.c_ubyte * 128)(*t.cpu().tolist())
         self.check(self.lib.tbslas_b200_comm_init(self.h, world, rank, buf))
 
+    def comm_last_exchange(self):
+        """(sent, received) outsider points of the most recent tree evaluation."""
+        a, b = C.c_size_t(), C.c_size_t()
+        self.check(self.lib.tbslas_b200_comm_last_exchange(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def comm_rank(self):
         r, n = C.c_int(), C.c_int()
         self.check(self.lib.tbslas_b200_comm_rank(self.h, C.byref(r), C.byref(n)))

@@ -85,10 +85,11 @@ static const char *kStageNames[ST_COUNT] = {"H2D",     "D2H",       "Locate", "B
                                             "Exchange", "Unpack",    "GridPoints"};
 
 // multi-rank pieces (comm.cu)
-int comm_tree_splitters(tbslas_tree *t);
-int comm_eval_outsiders(tbslas_tree *t, int bc, const double *pos, size_t n, const int32_t *leaf,
-                        const uint32_t *rank, const uint32_t *send_count_dev, int epilogue,
-                        double *out, const double *base, double alpha, int32_t *leaf_out);
+int comm_tree_splitters(tbslas_tree *t, uint64_t first_key);
+int comm_begin_exchange(tbslas_ctx *ctx, const uint32_t *send_count_dev);
+int comm_finish_exchange(tbslas_tree *t, int bc, const double *send_pos, const uint32_t *send_idx,
+                         int epilogue, double *out, const double *base, double alpha,
+                         int32_t *leaf_out);
 void comm_destroy(tbslas_ctx *ctx);
 
 // ---------------------------------------------------------------------------
@@ -108,6 +109,7 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
                 TBSLAS_MAX_CHEB_DEG);
   const size_t max_tiles = n / tile_pts + t->n_leaf + 2;
   void *leaf, *rank, *count, *bin_start, *tile_start, *tile_map, *perm, *send_count = nullptr;
+  void *send_pos = nullptr, *send_idx = nullptr;
   TB_TRY(ws_get(ctx, WS_LEAF, sizeof(int32_t) * (n + 1), &leaf));
   TB_TRY(ws_get(ctx, WS_RANK, sizeof(uint32_t) * (n + 1), &rank));
   TB_TRY(ws_get(ctx, WS_PERM, sizeof(uint32_t) * (n + 1), &perm));
@@ -116,7 +118,12 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   TB_TRY(ws_get(ctx, WS_TILESTART, sizeof(uint32_t) * (t->n_leaf + 2), &tile_start));
   TB_TRY(ws_get(ctx, WS_TILELEAF, sizeof(int2) * max_tiles, &tile_map));
   const bool multi = allow_exchange && ctx->nranks > 1;
-  if (multi) send_count = (uint32_t *)count + t->n_leaf + 2;
+  if (multi) {
+    send_count = (uint32_t *)count + t->n_leaf + 2;
+    // worst case: every point is an outsider (sizes must be known before the counts are)
+    TB_TRY(ws_get(ctx, WS_SEND, sizeof(double) * 3 * (n + 1), &send_pos));
+    TB_TRY(ws_get(ctx, WS_SENDIDX, sizeof(uint32_t) * (n + 1), &send_idx));
+  }
 
   LocateArgs la;
   la.tree = t;
@@ -128,6 +135,7 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   la.count = (uint32_t *)count;
   la.send_count = (uint32_t *)send_count;
   TB_TRY(launch_locate(ctx, la));
+  if (multi) TB_TRY(comm_begin_exchange(ctx, (const uint32_t *)send_count));
 
   BinArgs ba;
   ba.n_leaf = t->n_leaf;
@@ -141,7 +149,15 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   ba.tile_map = (int2 *)tile_map;
   ba.perm = (uint32_t *)perm;
   ba.max_tiles = max_tiles;
+  if (multi) {
+    ba.pos = pos;
+    ba.send_count = (const uint32_t *)send_count;
+    ba.nranks = ctx->nranks;
+    ba.send_pos = (double *)send_pos;
+    ba.send_idx = (uint32_t *)send_idx;
+  }
   TB_TRY(launch_bin(ctx, ba));
+  if (multi) TB_CUDA(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
 
   EvalArgs ea;
   ea.tree = t;
@@ -164,8 +180,8 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
     TB_TRY(launch_leaf_fixup(ctx, leaf_out, n, t->n_leaf, t->leaf_offset));
   }
   if (multi)
-    TB_TRY(comm_eval_outsiders(t, bc, pos, n, (const int32_t *)leaf, (const uint32_t *)rank,
-                               (const uint32_t *)send_count, epilogue, out, base, alpha, leaf_out));
+    TB_TRY(comm_finish_exchange(t, bc, (const double *)send_pos, (const uint32_t *)send_idx, epilogue,
+                                out, base, alpha, leaf_out));
   return TBSLAS_OK;
 }
 
@@ -299,7 +315,7 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
     return TBSLAS_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
-  cudaMallocHost(&ctx->h_counts, sizeof(unsigned) * 4 * kMaxRanks);
+  cudaMallocHost(&ctx->h_counts, sizeof(unsigned) * kMaxRanks * kMaxRanks);
   *out = ctx;
   return TBSLAS_OK;
 }
@@ -345,7 +361,10 @@ int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   if (q < 1 || q > TBSLAS_MAX_CHEB_DEG)
     return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "Chebyshev degree %d not supported (1..%d)", q,
                 TBSLAS_MAX_CHEB_DEG);
-  if (dof < 1 || dof > 16 || n_leaf < 1 || n_leaf > 0x7ffffff0u || !coord || !depth || !coeff)
+  // a rank of a multi-rank context may own no leaf of this tree (empty Morton range)
+  const size_t min_leaf = ctx->nranks > 1 ? 0 : 1;
+  if (dof < 1 || dof > 16 || n_leaf < min_leaf || n_leaf > 0x7ffffff0u ||
+      (n_leaf && (!coord || !depth || !coeff)))
     return fail(ctx, TBSLAS_ERR_INVALID, "tree_create: bad argument (dof=%d, n_leaf=%zu)", dof, n_leaf);
   TB_CUDA(ctx, cudaSetDevice(ctx->device));
   // geometry and keys are built on the host (n_leaf is small next to the points)
@@ -388,20 +407,20 @@ int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
     if (e_ != cudaSuccess)                                                                   \
       return bail(fail(ctx, TBSLAS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)));      \
   } while (0)
-  TB_TREE_CUDA(cudaMalloc(&t->d_key, sizeof(uint64_t) * n_leaf));
+  TB_TREE_CUDA(cudaMalloc(&t->d_key, sizeof(uint64_t) * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMalloc(&t->d_geom, sizeof(double4) * (n_leaf + 1)));
-  TB_TREE_CUDA(cudaMalloc(&t->d_depth, n_leaf));
+  TB_TREE_CUDA(cudaMalloc(&t->d_depth, n_leaf + 1));
   TB_TREE_CUDA(cudaMalloc(&t->d_coeff, sizeof(double) * t->stride * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMemcpy(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice));
   TB_TREE_CUDA(cudaMemcpy(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice));
   TB_TREE_CUDA(cudaMemcpy(t->d_depth, hd.data(), n_leaf, cudaMemcpyHostToDevice));
   TB_TREE_CUDA(cudaMemset(t->d_coeff, 0, sizeof(double) * t->stride * (n_leaf + 1)));
 #undef TB_TREE_CUDA
-  t->splitters.assign(1, hk[0]);
-  int rc = tbslas_b200_tree_update_coeff(t, coeff, mem);
+  t->splitters.assign(1, n_leaf ? hk[0] : ~0ull);
+  int rc = n_leaf ? tbslas_b200_tree_update_coeff(t, coeff, mem) : TBSLAS_OK;
   if (rc != TBSLAS_OK) return bail(rc);
   if (ctx->nranks > 1) {
-    rc = comm_tree_splitters(t);
+    rc = comm_tree_splitters(t, n_leaf ? hk[0] : ~0ull);
     if (rc != TBSLAS_OK) return bail(rc);
   }
   *out = t;

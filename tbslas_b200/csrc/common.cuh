@@ -58,6 +58,9 @@ enum Slot {
   WS_SENDVAL,
   WS_RECVVAL,
   WS_SENDIDX,
+  WS_COUNTMAT,   // uint32 [nranks][nranks] send-count matrix
+  WS_RECVLEAF,   // int32 leaf ids of received points / returned to the origin
+  WS_RETLEAF,
   WS_MISC,
   WS_COUNT_SLOTS
 };
@@ -88,7 +91,10 @@ struct tbslas_ctx {
   // communicator (single rank unless comm_init was called)
   int rank = 0, nranks = 1;
   void *nccl_comm = nullptr;
-  // pinned host scratch for small device->host reads (exchange counts)
+  cudaStream_t comm_stream = nullptr;  // NCCL traffic that overlaps the insider evaluation
+  cudaEvent_t ev_comm = nullptr, ev_counts = nullptr, ev_packed = nullptr;
+  size_t last_sent = 0, last_recv = 0;  // outsiders of the most recent tree evaluation
+  // pinned host scratch for small device->host reads (exchange counts: [nranks][nranks])
   unsigned *h_counts = nullptr;
 };
 
@@ -160,6 +166,12 @@ struct BinArgs {
   int2 *tile_map;         // [max_tiles] {leaf, first slot}
   uint32_t *perm;         // [n] point ids grouped by leaf
   size_t max_tiles;
+  // multi-rank only (send_count != nullptr): outsiders are packed into per-owner buckets
+  const double *pos = nullptr;
+  const uint32_t *send_count = nullptr;  // [nranks]
+  int nranks = 1;
+  double *send_pos = nullptr;            // [n_out][3]
+  uint32_t *send_idx = nullptr;          // [n_out] origin index of each packed point
 };
 int launch_bin(tbslas_ctx *ctx, const BinArgs &a);
 

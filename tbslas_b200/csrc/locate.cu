@@ -317,14 +317,39 @@ __global__ void tile_map_kernel(const uint32_t *__restrict__ bin_start,
   tile_map[t] = make_int2(lo, (int)(__ldg(bin_start + lo) + (t - __ldg(tile_start + lo)) * tile_pts));
 }
 
+// Insiders: point id -> its slot in the leaf grouping.  Outsiders (MULTI): coordinates and
+// origin index -> the send bucket of the owner rank (reference: the forward scatter of
+// par::ScatterForward, tree_functor.h:574-575); bucket offsets = exclusive scan of the
+// per-rank send counts, rebuilt per CTA in shared memory (nranks <= 64).
+template <bool MULTI>
 __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint32_t *__restrict__ rank,
                                     const uint32_t *__restrict__ bin_start, size_t n,
-                                    uint32_t *__restrict__ perm) {
+                                    uint32_t *__restrict__ perm, const double *__restrict__ pos,
+                                    const uint32_t *__restrict__ send_count, int nranks,
+                                    double *__restrict__ send_pos, uint32_t *__restrict__ send_idx) {
+  __shared__ unsigned s_off[kMaxRanks];
+  if (MULTI) {
+    if (threadIdx.x == 0) {
+      unsigned run = 0;
+      for (int r = 0; r < nranks; r++) {
+        s_off[r] = run;
+        run += __ldg(send_count + r);
+      }
+    }
+    __syncthreads();
+  }
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int j = leaf[i];
-  if (j < 0) return;  // outsider: travels to its owner instead
-  perm[__ldg(bin_start + j) + rank[i]] = (uint32_t)i;
+  if (j >= 0) {
+    perm[__ldg(bin_start + j) + rank[i]] = (uint32_t)i;
+  } else if (MULTI) {  // travels to its owner
+    const unsigned slot = s_off[-2 - j] + rank[i];
+    send_pos[3 * (size_t)slot] = pos[3 * i];
+    send_pos[3 * (size_t)slot + 1] = pos[3 * i + 1];
+    send_pos[3 * (size_t)slot + 2] = pos[3 * i + 2];
+    send_idx[slot] = (uint32_t)i;
+  }
 }
 
 int launch_bin(tbslas_ctx *ctx, const BinArgs &a) {
@@ -338,7 +363,13 @@ int launch_bin(tbslas_ctx *ctx, const BinArgs &a) {
   TB_CUDA(ctx, cudaGetLastError());
   if (a.n) {
     const unsigned grid = (unsigned)((a.n + 255) / 256);
-    scatter_perm_kernel<<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.perm);
+    if (a.send_count)
+      scatter_perm_kernel<true><<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.perm,
+                                                             a.pos, a.send_count, a.nranks,
+                                                             a.send_pos, a.send_idx);
+    else
+      scatter_perm_kernel<false><<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.perm,
+                                                              nullptr, nullptr, 1, nullptr, nullptr);
     TB_CUDA(ctx, cudaGetLastError());
   }
   return TBSLAS_OK;

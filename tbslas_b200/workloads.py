@@ -152,14 +152,26 @@ def flops_per_point_step(q: int, n_vel_trees: int = 1) -> int:
     return 2 * n_vel_trees * flops_per_point_eval(q, 3) + flops_per_point_eval(q, 1) + 18
 
 
-def shard_with_splitters(ft: ftm.FlatTree, splitters: np.ndarray, rank: int) -> ftm.FlatTree:
-    """Leaves of `ft` whose key range intersects rank's Morton range [s_r, s_{r+1}) -- the
-    co-partition the reference obtains with MergeTree (tree_utils.h:703-728).  A coarse leaf
-    straddling a splitter is present on both ranks."""
-    keys = ft.keys()
-    nxt = np.concatenate([keys[1:], np.array([np.iinfo(np.uint64).max], dtype=np.uint64)])
-    lo = splitters[rank] if rank > 0 else np.uint64(0)
-    hi = splitters[rank + 1] if rank + 1 < len(splitters) else np.iinfo(np.uint64).max
-    sel = (nxt > lo) & (keys < hi)
-    idx = np.nonzero(sel)[0]
+def partition_leaves(n_leaf: int, nranks: int) -> np.ndarray:
+    """Equal-count contiguous Morton ranges: first[r] = r*n_leaf//nranks (what PVFMM's
+    RedistNodes gives a uniform-weight tree); mirrors tbslas_b200_partition_leaves."""
+    return np.array([r * n_leaf // nranks for r in range(nranks + 1)], dtype=np.int64)
+
+
+def owner_of_keys(keys: np.ndarray, splitters: np.ndarray) -> np.ndarray:
+    """Owner rank of each key: last r with splitters[r] <= key, rank 0 below the first
+    (tree_functor.h:491-513 / the split-key rule of par::SortScatterIndex)."""
+    return np.maximum(np.searchsorted(splitters, keys, side="right") - 1, 0)
+
+
+def shard_by_splitters(ft: ftm.FlatTree, splitters: np.ndarray, rank: int) -> ftm.FlatTree:
+    """The leaves of `ft` that rank `rank` owns when the tree is re-partitioned with the
+    given break points -- whole leaves, assigned by their own Morton id, as PVFMM's
+    RedistNodes does after tbslas::MergeTree computed common break points for the velocity
+    and the scalar tree (tree_utils.h:703-728).  May be empty."""
+    own = owner_of_keys(ft.keys(), np.asarray(splitters, dtype=np.uint64))
+    idx = np.nonzero(own == rank)[0]
+    if idx.size == 0:
+        return ft.shard(0, 0)
+    assert idx[-1] - idx[0] + 1 == idx.size  # contiguous by construction
     return ft.shard(int(idx[0]), int(idx[-1]) + 1)

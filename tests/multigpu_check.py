@@ -1,0 +1,137 @@
+"""Multi-GPU parity check, one rank per GPU (not collected by pytest; launched by
+tests/test_multigpu.py or by hand):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29517 tests/multigpu_check.py
+
+Every rank holds a contiguous Morton range of each tree (whole leaves, as an MPI rank of the
+reference does), evaluates ITS OWN points through the sharded trees -- outsiders travel by
+NCCL all-to-all-v inside the library -- and compares with the same points evaluated on the
+FULL tree by a single-rank context on the same GPU.  The evaluation of a point depends only
+on the leaf that contains it, so the results must be BIT-IDENTICAL (values, leaf ids,
+departure points), whatever the partition.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from tbslas_b200 import api, workloads
+    from tbslas_b200 import flat_tree as ftm
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = api.Context(local)
+    ctx.comm_init_torch()
+    assert ctx.comm_rank() == (rank, world)
+    solo = api.Context(local)  # single-rank context on the same GPU: the full trees
+
+    def refine(lower, edge, d):
+        c = lower + 0.5 * edge[:, None]
+        r = np.sqrt(((c - np.array([0.55, 0.5, 0.45])) ** 2).sum(axis=1))
+        return np.abs(r - 0.3) < edge
+    coord, dd = ftm.adaptive_leaves(refine, 2, 5)
+    q = 6
+    con = ftm.fit(coord, dd, q, 1, lambda p: ftm.gaussian(p, (0.5, 0.5, 0.5), 0.2))
+    vc, vd = ftm.uniform_leaves(2)
+    vels = [ftm.fit(vc, vd, q, 3, lambda p, s=s: s * (ftm.vel_rotation(p) + 0.1 * ftm.vel_taylor_green(p)))
+            for s in (0.8, 1.0, 1.1, 1.3)]
+    times = [-0.05, 0.0, 0.05, 0.1]
+
+    first = workloads.partition_leaves(con.n_leaf, world)
+    splitters = con.keys()[first[:-1]]
+    con_l = con.shard(int(first[rank]), int(first[rank + 1]))
+    vel_l = [workloads.shard_by_splitters(v, splitters, rank) for v in vels]
+    tcon, tvel = ctx.tree(con_l), [ctx.tree(v) for v in vel_l]
+    scon, svel = solo.tree(con), [solo.tree(v) for v in vels]
+    checks = []
+
+    def same(name, a, b):
+        ok = np.array_equal(a, b)
+        checks.append((name, ok))
+        if not ok:
+            d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))
+            print("[rank %d] MISMATCH %s: max abs diff %g at %d of %d entries" %
+                  (rank, name, d.max(), int((d != 0).sum()), d.size), flush=True)
+
+    # (1) arbitrary points (different on every rank, most of them outsiders), both bcs
+    rng = np.random.default_rng(100 + rank)
+    n = 40000 + 1000 * rank
+    pts = np.concatenate([rng.uniform(-0.05, 1.05, size=(n, 3)), rng.integers(0, 33, size=(500, 3)) / 32.0])
+    for bc in (0, 1):
+        f, g = api.NodeFieldFunctor(tcon), api.NodeFieldFunctor(scon)
+        pa, pb = pts.copy(), pts.copy()
+        va, la = f.eval_with_leaf(pa, bc)
+        sent, recv = ctx.comm_last_exchange()
+        vb, lb = g.eval_with_leaf(pb, bc)
+        same("eval values bc%d" % bc, va, vb)
+        same("eval leaf ids bc%d" % bc, la, lb)
+        same("eval wrapped positions bc%d" % bc, pa, pb)
+        checks.append(("outsiders exist bc%d" % bc, world == 1 or sent > 0))
+        f3, g3 = api.NodeFieldFunctor(tvel[1]), api.NodeFieldFunctor(svel[1])
+        same("eval dof3 bc%d" % bc, f3(pts.copy(), bc=bc), g3(pts.copy(), bc=bc))
+
+    # (2) the semi-Lagrangian step on this rank's own arrival points, host and device buffers
+    arr = ftm.grid_points(con_l.coord, con_l.depth, q)
+    for bc in (0, 1):
+        for nrk in (1, 2):
+            vel, con_f = api.NodeFieldFunctor(tvel[1]), api.NodeFieldFunctor(tcon)
+            svel_f, scon_f = api.NodeFieldFunctor(svel[1]), api.NodeFieldFunctor(scon)
+            da, db = np.empty_like(arr), np.empty_like(arr)
+            a = api.SolveSemilagRK2(vel, con_f, arr, 3, 0.05, nrk, bc, departure_points=da)
+            b = api.SolveSemilagRK2(svel_f, scon_f, arr, 3, 0.05, nrk, bc, departure_points=db)
+            same("semilag values bc%d nrk%d" % (bc, nrk), a, b)
+            same("semilag departure points bc%d nrk%d" % (bc, nrk), da, db)
+    d_arr = torch.from_numpy(arr).cuda()
+    ctx.set_stream(torch.cuda.current_stream())
+    d_val = api.SolveSemilagRK2(api.NodeFieldFunctor(tvel[1]), api.NodeFieldFunctor(tcon), d_arr, 3, 0.05, 1, 1)
+    torch.cuda.synchronize()
+    ctx.set_stream(None)
+    same("semilag device buffers", d_val.cpu().numpy(),
+         api.SolveSemilagRK2(api.NodeFieldFunctor(svel[1]), api.NodeFieldFunctor(scon), arr, 3, 0.05, 1, 1))
+
+    # (3) time-varying and extrapolated velocity functors
+    fset, gset = api.FieldSetFunctor(tvel, times), api.FieldSetFunctor(svel, times)
+    same("set4 eval", fset(pts.copy(), time=0.02, bc=1), gset(pts.copy(), time=0.02, bc=1))
+    same("set4 trajectory", api.ComputeTrajRK2(fset, arr, 0.05, 0.0, 2, 1),
+         api.ComputeTrajRK2(gset, arr, 0.05, 0.0, 2, 1))
+    fext, gext = api.FieldExtrapFunctor(tvel[0], tvel[1]), api.FieldExtrapFunctor(svel[0], svel[1])
+    same("extrap trajectory",
+         api.ComputeTrajRK2(api.NodeFieldFunctor(tvel[1]), arr, 0.05, 0.0, 1, 0, extrap_fn=fext),
+         api.ComputeTrajRK2(api.NodeFieldFunctor(svel[1]), arr, 0.05, 0.0, 1, 0, extrap_fn=gext))
+
+    # (4) a tree with fewer leaves than ranks: the last rank(s) own nothing
+    one_c, one_d = ftm.uniform_leaves(0)
+    one = ftm.random_tree(one_c, one_d, 5, 2, seed=5)
+    t1 = ctx.tree(one if rank == 0 else one.shard(0, 0))
+    s1 = solo.tree(one)
+    same("single-leaf tree", api.NodeFieldFunctor(t1)(pts.copy(), bc=0), api.NodeFieldFunctor(s1)(pts.copy(), bc=0))
+    # (5) empty point set on one rank (the call is still collective)
+    e = pts[:0].copy() if rank == world - 1 else pts[:777].copy()
+    same("ragged: empty input on the last rank", api.NodeFieldFunctor(tcon)(e.copy(), bc=0),
+         api.NodeFieldFunctor(scon)(e.copy(), bc=0))
+
+    ok = all(c[1] for c in checks)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("multigpu_check: %d ranks, %d checks per rank, %s" %
+              (world, len(checks), "ALL BIT-IDENTICAL" if flag.item() else "FAILED"), flush=True)
+    dist.barrier()
+    ctx.close()
+    solo.close()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+// tools/evalbench.cu -- steady-state rate of the Chebyshev contraction (no gathers, no
+// tile prologue): the inner loops of cheb_eval.cuh run `iters` times per thread over two
+// alternating coefficient blocks resident in shared memory.  Separates "the inner loop
+// itself" from "tile prologue / occupancy" when reading the eval kernel's FP64-pipe
+// utilisation.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+//        -Itbslas_b200/csrc -Iinclude tools/evalbench.cu -o tools/evalbench
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "cheb_eval.cuh"
+
+using namespace tb;
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);  \
+      exit(1);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+template <int Q, int PPT, bool PYS, bool PAIR, int MINB>
+__global__ void __launch_bounds__(kEvalThreads, MINB)
+steady_kernel(const double *__restrict__ coef, unsigned stride, double *__restrict__ out, int iters) {
+  constexpr int D = Q + 1;
+  extern __shared__ __align__(128) double s_coef[];
+  for (unsigned i = threadIdx.x; i < 2 * stride; i += blockDim.x) s_coef[i] = coef[i];
+  double *s_py = s_coef + 2 * stride + threadIdx.x;
+  __syncthreads();
+  double px[PPT][D], py[PYS ? 1 : PPT][D], zc[PPT], z0[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; s++) {
+    const double xi = -0.9 + 1.7e-3 * threadIdx.x + 0.11 * s, yi = 0.8 - 2.1e-3 * threadIdx.x - 0.07 * s;
+    cheb_basis<Q>(xi, px[s]);
+    if (PYS) {
+      cheb_basis<Q>(yi, py[0]);
+#pragma unroll
+      for (int j = 0; j < D; j++) s_py[(j * PPT + s) * kEvalThreads] = py[0][j];
+    } else {
+      cheb_basis<Q>(yi, py[s]);
+    }
+    zc[s] = 0.3 - 1e-3 * threadIdx.x;
+    z0[s] = 1.0;
+  }
+  double acc[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; s++) acc[s] = 0;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    const double2 *C2 = reinterpret_cast<const double2 *>(s_coef + (it & 1) * stride);
+    double u[PPT], tz0[PPT], tz1[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) u[s] = tz0[s] = tz1[s] = 0.0;
+    ZLevel<Q, PPT, PYS, PAIR, 0, 0>::run(C2, px, py, s_py, zc, z0, tz0, tz1, u);
+#pragma unroll
+    for (int s = 0; s < PPT; s++) acc[s] += u[s];
+  }
+  double r = 0;
+#pragma unroll
+  for (int s = 0; s < PPT; s++) r += acc[s];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+template <int Q, int PPT, bool PYS, bool PAIR, int MINB>
+void run(const char *name, int ctas_per_sm, int n_sm, const double *d_coef, double *d_out) {
+  constexpr int D = Q + 1;
+  const unsigned ncoef = D * (D + 1) * (D + 2) / 6, stride = ncoef + (ncoef & 1);
+  const size_t smem = (2 * stride + (PYS ? (size_t)D * PPT * kEvalThreads : 0)) * sizeof(double);
+  auto k = steady_kernel<Q, PPT, PYS, PAIR, MINB>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kEvalThreads, smem));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, k));
+  const int iters = 400, grid = n_sm * ctas_per_sm;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0));
+    k<<<grid, kEvalThreads, smem>>>(d_coef, stride, d_out, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep && ms < best) best = ms;
+  }
+  const double dfma = (double)(ncoef + D * (D + 1) / 2 + D) * PPT * kEvalThreads * (double)grid * iters;
+  printf("%-28s q=%d ppt=%d pys=%d pair=%d regs=%3d occ=%d ctas/sm=%d : %.3f ms  %.2f TFLOP/s (executed DFMA)\n",
+         name, Q, PPT, (int)PYS, (int)PAIR, fa.numRegs, occ, ctas_per_sm, best, 2 * dfma / best * 1e-9);
+}
+
+int main() {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  const int n_sm = prop.multiProcessorCount;
+  std::vector<double> h(4096);
+  for (size_t i = 0; i < h.size(); i++) h[i] = 1e-3 * ((i * 2654435761u) % 1000) - 0.5;
+  double *d_coef, *d_out;
+  CK(cudaMalloc(&d_coef, h.size() * 8));
+  CK(cudaMemcpy(d_coef, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_out, sizeof(double) * kEvalThreads * n_sm * 8));
+  printf("device %s, %d SMs\n", prop.name, n_sm);
+  // occupancy sweep of the shipped q=14 shape (255 regs -> 2 CTAs/SM)
+  run<14, 2, false, false, 1>("ppt2 regs", 1, n_sm, d_coef, d_out);
+  run<14, 2, false, false, 1>("ppt2 regs", 2, n_sm, d_coef, d_out);
+  run<14, 2, false, true, 1>("ppt2 regs pair", 1, n_sm, d_coef, d_out);
+  run<14, 2, false, true, 1>("ppt2 regs pair", 2, n_sm, d_coef, d_out);
+  run<14, 2, false, false, 3>("ppt2 regs minb3", 3, n_sm, d_coef, d_out);
+  run<14, 2, true, false, 3>("ppt2 pys minb3", 3, n_sm, d_coef, d_out);
+  run<14, 2, true, false, 4>("ppt2 pys minb4", 4, n_sm, d_coef, d_out);
+  run<14, 3, false, false, 1>("ppt3 regs", 2, n_sm, d_coef, d_out);
+  run<14, 3, true, false, 1>("ppt3 pys", 2, n_sm, d_coef, d_out);
+  run<14, 3, true, false, 3>("ppt3 pys minb3", 3, n_sm, d_coef, d_out);
+  run<14, 4, true, false, 1>("ppt4 pys", 2, n_sm, d_coef, d_out);
+  run<14, 4, true, true, 1>("ppt4 pys pair", 2, n_sm, d_coef, d_out);
+  run<8, 4, false, false, 1>("q8 ppt4 regs", 2, n_sm, d_coef, d_out);
+  run<8, 4, false, false, 3>("q8 ppt4 regs minb3", 3, n_sm, d_coef, d_out);
+  run<8, 4, false, false, 4>("q8 ppt4 regs minb4", 4, n_sm, d_coef, d_out);
+  return 0;
+}
