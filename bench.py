@@ -198,18 +198,17 @@ def run_b200(args):
     ctx.set_stream(torch.cuda.current_stream())
     if world > 1:
         ctx.comm_init_torch()
-        first = [r * wl.con.n_leaf // world for r in range(world + 1)]
-        keys = wl.con.keys()
-        splitters = keys[np.array(first[:-1])]
-        con_local = wl.con.shard(first[rank], first[rank + 1])
-        vel_local = [workloads.shard_with_splitters(v, splitters, rank) for v in wl.vel]
+        # the advected tree in equal-count contiguous Morton ranges; the velocity tree
+        # re-partitioned with the SAME break points, whole leaves by their own Morton id
+        # (what tbslas::MergeTree + RedistNodes do, tree_utils.h:703-728)
+        first = workloads.partition_leaves(wl.con.n_leaf, world)
+        splitters = wl.con.keys()[first[:-1]]
+        con_local = wl.con.shard(int(first[rank]), int(first[rank + 1]))
+        vel_local = [workloads.shard_by_splitters(v, splitters, rank) for v in wl.vel]
     else:
         con_local, vel_local = wl.con, wl.vel
     tcon = ctx.tree(con_local)
     tvel = [ctx.tree(v) for v in vel_local]
-    if world > 1:
-        for t in tvel:
-            t.copartition(tcon)
     con_f = api.NodeFieldFunctor(tcon)
     vel_f = api.NodeFieldFunctor(tvel[0]) if len(tvel) == 1 else api.FieldSetFunctor(tvel, wl.vel_times)
 
@@ -250,6 +249,7 @@ def run_b200(args):
     barrier()
     sampler.mark_end()
     ms = e0.elapsed_time(e1)
+    exch = ctx.comm_last_exchange() if world > 1 else (0, 0)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.kernel_launches() - launches0
     prof = ctx.profile()
@@ -330,7 +330,11 @@ def run_b200(args):
                    "l2_policy": "inputs (%.1f GB of points per step) exceed the 126 MB L2" %
                                 (n_local * 24 / 1e9),
                    "partition": "single GPU" if world == 1 else
-                                "equal-count contiguous Morton ranges, co-partitioned velocity tree"},
+                                "equal-count contiguous Morton ranges of the advected tree; velocity "
+                                "tree re-partitioned with the same break points (whole leaves)",
+                   "exchange": None if world == 1 else
+                   {"collective": "NCCL all-to-all-v (grouped send/recv), forward xyz + reverse values",
+                    "rank0_last_eval_sent": exch[0], "rank0_last_eval_received": exch[1]}},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": n_total / e2e_s, "unit": "points/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(n_local * 24), "d2h_bytes_per_step": int(n_local * 8),

@@ -148,6 +148,15 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2,
                             int timestep, double dt, int nrk, double *out_vals,
                             double *out_dep, int mem);
 
+/* Steps (1)+(2) of tbslas::SolveSemilagInSitu (tree_semilag.h:92-130): the arrival points
+ * are the Chebyshev grid points of `con`'s own (local) leaves, generated in HBM
+ * (CollectChebTreeGridPoints, tree_utils.h:442-498) -- no 24 B/point host->device copy --
+ * then semilag_rk2.  out_vals[n_leaf*(q+1)^3][dof_con], leaf-major, ready for
+ * SetTreeGridValues (tree_utils.h:500-552). */
+int tbslas_b200_semilag_insitu(const tbslas_field *f1, const tbslas_field *f2,
+                               tbslas_tree *con, int bc, int timestep, double dt, int nrk,
+                               double *out_vals, int mem);
+
 /* ---- uniform-grid cubic variant (tbslas::fast_interp, tree_functor.h:89-153) - */
 /* grid [dof][n_reg][n_reg][n_reg] (x fastest), node centred on [0,1]^3. */
 int tbslas_b200_cubic_eval(tbslas_ctx *ctx, const double *grid, int n_reg, int dof,

@@ -474,7 +474,26 @@ inline int ScatterReverse(Vector<T> &, const Vector<size_t> &, const MPI_Comm &,
                           size_t = 0) {
   return 0;
 }
+// Declared only so that tree_utils.h / tree_semilag.h parse (non-dependent names);
+// they belong to tree construction, merging and curl, which are outside the hot path and
+// are never called through this stand-in.
+template <class V, class W>
+inline int HyperQuickSort(const V &, W &, const MPI_Comm &) {
+  abort();
+}
+template <class T, class V>
+inline int partitionW(V &, unsigned int *, const MPI_Comm &) {
+  abort();
+}
 }  // namespace par
+template <class T, class Y>
+inline T cheb_approx(T *, int, int, T *, void * = NULL) {
+  abort();
+}
+template <class T>
+inline void cheb_curl(T *, int, T *, void * = NULL) {
+  abort();
+}
 
 // -------------------------------------------------------------- tree / nodes
 template <class Real>

@@ -312,6 +312,23 @@ def SolveSemilagRK2(vel_evaluator: _Functor, con_evaluator: NodeFieldFunctor, po
     return points_vals
 
 
+def SolveSemilagInSitu(tvel_func: _Functor, tree_curr: Tree, timestep: int, dt: float,
+                       num_rk_step: int = 1, bc: int = FREESPACE,
+                       tvel_extrap: Optional[_Functor] = None, device: bool = False):
+    """Steps (1)+(2) of tbslas::SolveSemilagInSitu (tree_semilag.h:92-130): the arrival points
+    are generated in HBM from ``tree_curr``'s own leaves and advected; returns the new grid
+    values [n_leaf*(q+1)^3, dof] (leaf-major), the input of SetTreeGridValues."""
+    n = tree_curr.n_leaf * (tree_curr.q + 1) ** 3
+    out = (torch.empty((n, tree_curr.dof), dtype=torch.float64, device="cuda:%d" % tree_curr.ctx.device)
+           if device else np.empty((n, tree_curr.dof)))
+    a, m = _addr(out)
+    ctx = tree_curr.ctx
+    ctx.check(ctx.lib.tbslas_b200_semilag_insitu(
+        C.byref(tvel_func.field), C.byref(tvel_extrap.field) if tvel_extrap is not None else None,
+        tree_curr.h, bc, int(timestep), float(dt), int(num_rk_step), a, m))
+    return out
+
+
 def new_nodes(q: int) -> np.ndarray:
     """tbslas::new_nodes 1-D table (cheb.h:51-58)."""
     out = (C.c_double * (q + 1))()

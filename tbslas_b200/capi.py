@@ -27,7 +27,7 @@ SYMBOLS = [
     "tbslas_b200_tree_create", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_destroy",
     "tbslas_b200_tree_info", "tbslas_b200_eval", "tbslas_b200_eval_set4",
     "tbslas_b200_eval_extrap", "tbslas_b200_eval_field", "tbslas_b200_traj_rk2",
-    "tbslas_b200_semilag_rk2", "tbslas_b200_cubic_eval", "tbslas_b200_collect_grid_points",
+    "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_cubic_eval", "tbslas_b200_collect_grid_points",
     "tbslas_b200_new_nodes", "tbslas_b200_point_key", "tbslas_b200_owner_of_key",
     "tbslas_b200_partition_leaves", "tbslas_b200_profile_enable", "tbslas_b200_profile_reset",
     "tbslas_b200_profile_num_stages", "tbslas_b200_profile_stage_name",
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
                                        C.c_double, C.c_double, C.c_int, dp, C.c_int]
     L.tbslas_b200_semilag_rk2.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int, dp,
                                           sz, C.c_int, C.c_double, C.c_int, dp, dp, C.c_int]
+    L.tbslas_b200_semilag_insitu.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int,
+                                             C.c_int, C.c_double, C.c_int, dp, C.c_int]
     L.tbslas_b200_cubic_eval.argtypes = [vp, dp, C.c_int, C.c_int, dp, sz, dp, C.c_int]
     L.tbslas_b200_collect_grid_points.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_new_nodes.argtypes = [C.c_int, C.POINTER(C.c_double)]

@@ -548,9 +548,11 @@ int tbslas_b200_traj_rk2(const tbslas_field *f1, const tbslas_field *f2, int bc,
   return io.finish();
 }
 
-int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2, tbslas_tree *con, int bc,
-                            const double *pos, size_t n, int timestep, double dt, int nrk,
-                            double *out_vals, double *out_dep, int mem) {
+// pos == nullptr: the arrival points are generated on the device from `con`'s own leaves
+// (tbslas::CollectChebTreeGridPoints), i.e. steps (1)+(2) of tbslas::SolveSemilagInSitu.
+static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_tree *con, int bc,
+                        const double *pos, size_t n, int timestep, double dt, int nrk,
+                        double *out_vals, double *out_dep, int mem) {
   tbslas_ctx *ctx, *ctx2;
   int dof, dof2;
   TB_TRY(check_field(&ctx, f1, &dof));
@@ -560,7 +562,12 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2, tbsl
   }
   if (dof != 3) return fail(ctx, TBSLAS_ERR_INVALID, "velocity field must have dof 3 (got %d)", dof);
   if (!con || con->ctx != ctx) return fail(ctx, TBSLAS_ERR_INVALID, "advected tree missing");
-  if (nrk < 1 || (n && (!pos || !out_vals))) return fail(ctx, TBSLAS_ERR_INVALID, "bad argument");
+  const bool insitu = (pos == nullptr);
+  if (insitu) {
+    const size_t d = con->q + 1;
+    n = con->n_leaf * d * d * d;
+  }
+  if (nrk < 1 || (n && !out_vals)) return fail(ctx, TBSLAS_ERR_INVALID, "bad argument");
   const double tinit = timestep * dt;   // semilag.inc:34-35
   const double tfinal = tinit - dt;
   HostIO io{ctx, mem};
@@ -571,7 +578,9 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2, tbsl
     TB_TRY(ws_get(ctx, WS_POS_A, sizeof(double) * 3 * n, &xsol));
   TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * n, &xtmp));
   TB_TRY(io.out_buf(WS_VAL_B, out_vals, sizeof(double) * con->dof * n, &dval));
-  {
+  if (insitu) {
+    if (n) TB_TRY(launch_grid_points(ctx, con, (double *)xsol));
+  } else {
     StageScope sc(ctx, mem == TBSLAS_MEM_HOST ? ST_H2D : ST_COMBINE, (double)(24 * n), 0);
     TB_CUDA(ctx, cudaMemcpyAsync(xsol, pos, sizeof(double) * 3 * n,
                                  mem == TBSLAS_MEM_HOST ? cudaMemcpyHostToDevice
@@ -592,6 +601,22 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2, tbsl
   TB_TRY(eval_tree_dev(con, bc, (double *)xsol, n, EPI_STORE, (double *)dval, nullptr, 0.0, nullptr));
   TB_TRY(io.d2h(out_vals, dval, sizeof(double) * con->dof * n));
   return io.finish();
+}
+
+int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2, tbslas_tree *con, int bc,
+                            const double *pos, size_t n, int timestep, double dt, int nrk,
+                            double *out_vals, double *out_dep, int mem) {
+  if (n && !pos) {
+    tbslas_ctx *ctx = (f1 && f1->tree[0]) ? f1->tree[0]->ctx : nullptr;
+    return fail(ctx, TBSLAS_ERR_INVALID, "null point buffer");
+  }
+  static const double none[3] = {0, 0, 0};
+  return semilag_impl(f1, f2, con, bc, pos ? pos : none, n, timestep, dt, nrk, out_vals, out_dep, mem);
+}
+
+int tbslas_b200_semilag_insitu(const tbslas_field *f1, const tbslas_field *f2, tbslas_tree *con, int bc,
+                               int timestep, double dt, int nrk, double *out_vals, int mem) {
+  return semilag_impl(f1, f2, con, bc, nullptr, 0, timestep, dt, nrk, out_vals, nullptr, mem);
 }
 
 // ---------------------------------------------------------------- cubic grid

@@ -226,6 +226,36 @@ def test_gpu_device_resident_buffers(ctx, port):
     assert np.array_equal(dpts.cpu().numpy(), pts)  # arrival points are not modified
 
 
+def test_gpu_semilag_insitu_equals_explicit_points(ctx):
+    """tbslas_b200_semilag_insitu (arrival points generated in HBM) == semilag_rk2 on the
+    collected grid points, bit for bit."""
+    api = _api()
+    coord, dd = adaptive_leaves(4, 2)
+    tv = ftm.fit(coord, dd, 5, 3, ftm.vel_rotation)
+    tc = ftm.random_tree(coord, dd, 5, 2, seed=21)
+    tvel, tcon = ctx.tree(tv), ctx.tree(tc)
+    vel, con = api.NodeFieldFunctor(tvel), api.NodeFieldFunctor(tcon)
+    pts = tcon.collect_grid_points()
+    for bc in (0, 1):
+        a = api.SolveSemilagRK2(vel, con, pts, 2, 0.04, 2, bc)
+        b = api.SolveSemilagInSitu(vel, tcon, 2, 0.04, 2, bc)
+        assert np.array_equal(a, b)
+
+
+def test_gpu_cpp_dropin_binary():
+    """The reference's own C++ templates over the product's header-only adaptors
+    (oracle/dropin_test.cpp, prebuilt into oracle/_ref/ where /root/reference exists)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref",
+                       "dropin_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_test not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL OK" in r.stdout
+
+
 def test_gpu_grid_points_bit_exact(ctx, port):
     coord, dd = adaptive_leaves(4, 1)
     for q in (3, 8, 14):
