@@ -3,6 +3,7 @@
 // reference file:line each entry point replaces).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -288,6 +289,112 @@ struct HostIO {  // staging of caller buffers that live in host memory
   }
 };
 
+
+// ---------------------------------------------------------------------------
+// Host-buffer calls, pipelined: the points are cut into chunks and the H2D copy of chunk
+// c+1, the kernels of chunk c and the D2H copy of chunk c-1 run concurrently (copy-in
+// stream, the context's stream, copy-out stream; two buffer sets).  PCIe is full duplex and
+// a B200 has separate copy engines per direction, so a host call costs about
+// max(H2D, compute, D2H) instead of their sum.  Every chunk is a complete, independent
+// evaluation (the result of a point depends only on that point), so results are identical
+// to the one-shot path bit for bit.  In a multi-rank context every chunk is collective:
+// the chunk count must not depend on this rank's n.
+// ---------------------------------------------------------------------------
+struct PipeBufs {
+  double *pos, *tmp, *val;
+  int32_t *leaf;
+};
+struct PipeSpec {
+  const double *h_pos = nullptr;  // [n][3] input
+  double *h_pos_a = nullptr;      // positions after phase A (trajectory end points), optional
+  double *h_pos_b = nullptr;      // positions after phase B (periodic wrap written back), optional
+  double *h_val = nullptr;        // [n][val_dof], optional
+  int val_dof = 0;
+  int32_t *h_leaf = nullptr;      // [n], optional
+  bool need_tmp = false;
+};
+enum { EV_IN = 0, EV_A, EV_POSOUT, EV_B, EV_OUT };
+
+static int pipe_chunks(tbslas_ctx *ctx, size_t n) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("TBSLAS_HOST_CHUNKS");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) return forced;
+  if (ctx->nranks > 1) return 8;
+  const size_t k = n >> 20;  // >= 1 Mi points per chunk
+  return (int)(k < 1 ? 1 : (k > 16 ? 16 : k));
+}
+
+template <class FA, class FB>
+static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA phase_a, FB phase_b) {
+  const int K = pipe_chunks(ctx, n);
+  const size_t chunk = (n + K - 1) / K;
+  PipeBufs bufs[2] = {};
+  const Slot pos_slot[2] = {WS_POS_A, WS_POS_C}, val_slot[2] = {WS_VAL_B, WS_VAL_C},
+             leaf_slot[2] = {WS_LEAFOUT, WS_LEAFOUT2};
+  void *tmp = nullptr;
+  if (sp.need_tmp) TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * (chunk + 1), &tmp));
+  for (int b = 0; b < (K > 1 ? 2 : 1); b++) {
+    void *p, *v = nullptr, *l = nullptr;
+    TB_TRY(ws_get(ctx, pos_slot[b], sizeof(double) * 3 * (chunk + 1), &p));
+    if (sp.h_val) TB_TRY(ws_get(ctx, val_slot[b], sizeof(double) * sp.val_dof * (chunk + 1), &v));
+    if (sp.h_leaf) TB_TRY(ws_get(ctx, leaf_slot[b], sizeof(int32_t) * (chunk + 1), &l));
+    bufs[b] = PipeBufs{(double *)p, (double *)tmp, (double *)v, (int32_t *)l};
+  }
+  cudaStream_t s_in = ctx->copy_in, s_out = ctx->copy_out, s_run = ctx->stream;
+  auto ev = [&](int what, int b) { return ctx->ev_pipe[what][b]; };
+  // order the side streams after whatever the caller enqueued before this call
+  TB_CUDA(ctx, cudaEventRecord(ev(EV_OUT, 0), s_run));
+  TB_CUDA(ctx, cudaEventRecord(ev(EV_OUT, 1), s_run));
+  TB_CUDA(ctx, cudaEventRecord(ev(EV_B, 0), s_run));
+  TB_CUDA(ctx, cudaEventRecord(ev(EV_B, 1), s_run));
+  for (int c = 0; c < K; c++) {
+    const int b = c & 1;
+    const size_t off = (size_t)c * chunk;
+    const size_t m = off < n ? (n - off < chunk ? n - off : chunk) : 0;
+    PipeBufs &B = bufs[b];
+    // ---- copy in (buffer b is free once chunk c-2 has been computed and copied out)
+    TB_CUDA(ctx, cudaStreamWaitEvent(s_in, ev(EV_B, b), 0));
+    TB_CUDA(ctx, cudaStreamWaitEvent(s_in, ev(EV_OUT, b), 0));
+    if (m) TB_CUDA(ctx, cudaMemcpyAsync(B.pos, sp.h_pos + 3 * off, sizeof(double) * 3 * m,
+                                        cudaMemcpyHostToDevice, s_in));
+    TB_CUDA(ctx, cudaEventRecord(ev(EV_IN, b), s_in));
+    ctx->acc_units[ST_H2D] += (double)(24 * m);
+    // ---- compute
+    TB_CUDA(ctx, cudaStreamWaitEvent(s_run, ev(EV_IN, b), 0));
+    TB_TRY(phase_a(B, m));
+    if (sp.h_pos_a) {
+      TB_CUDA(ctx, cudaEventRecord(ev(EV_A, b), s_run));
+      TB_CUDA(ctx, cudaStreamWaitEvent(s_out, ev(EV_A, b), 0));
+      if (m) TB_CUDA(ctx, cudaMemcpyAsync(sp.h_pos_a + 3 * off, B.pos, sizeof(double) * 3 * m,
+                                          cudaMemcpyDeviceToHost, s_out));
+      TB_CUDA(ctx, cudaEventRecord(ev(EV_POSOUT, b), s_out));
+      TB_CUDA(ctx, cudaStreamWaitEvent(s_run, ev(EV_POSOUT, b), 0));  // phase B may wrap B.pos
+      ctx->acc_units[ST_D2H] += (double)(24 * m);
+    }
+    TB_TRY(phase_b(B, m));
+    TB_CUDA(ctx, cudaEventRecord(ev(EV_B, b), s_run));
+    // ---- copy out
+    TB_CUDA(ctx, cudaStreamWaitEvent(s_out, ev(EV_B, b), 0));
+    if (m && sp.h_val) {
+      TB_CUDA(ctx, cudaMemcpyAsync(sp.h_val + sp.val_dof * off, B.val, sizeof(double) * sp.val_dof * m,
+                                   cudaMemcpyDeviceToHost, s_out));
+      ctx->acc_units[ST_D2H] += (double)(8 * sp.val_dof * m);
+    }
+    if (m && sp.h_leaf)
+      TB_CUDA(ctx, cudaMemcpyAsync(sp.h_leaf + off, B.leaf, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s_out));
+    if (m && sp.h_pos_b)
+      TB_CUDA(ctx, cudaMemcpyAsync(sp.h_pos_b + 3 * off, B.pos, sizeof(double) * 3 * m,
+                                   cudaMemcpyDeviceToHost, s_out));
+    TB_CUDA(ctx, cudaEventRecord(ev(EV_OUT, b), s_out));
+  }
+  TB_CUDA(ctx, cudaStreamSynchronize(s_out));
+  TB_CUDA(ctx, cudaStreamSynchronize(s_run));
+  return TBSLAS_OK;
+}
+
 }  // namespace tb
 
 using namespace tb;
@@ -315,6 +422,10 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
     return TBSLAS_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
+  for (auto &pair : ctx->ev_pipe)
+    for (cudaEvent_t &e : pair) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaMallocHost(&ctx->h_counts, sizeof(unsigned) * kMaxRanks * kMaxRanks);
   *out = ctx;
   return TBSLAS_OK;
@@ -333,6 +444,11 @@ int tbslas_b200_finalize(tbslas_ctx *ctx) {
   }
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  for (auto &pair : ctx->ev_pipe)
+    for (cudaEvent_t &e : pair)
+      if (e) cudaEventDestroy(e);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return TBSLAS_OK;
@@ -470,14 +586,15 @@ int tbslas_b200_eval_field(const tbslas_field *f, double tq, int bc, double *pos
   int dof;
   TB_TRY(check_field(&ctx, f, &dof));
   if (n && (!pos || !out)) return fail(ctx, TBSLAS_ERR_INVALID, "null buffer");
-  HostIO io{ctx, mem};
-  void *dpos, *dout;
-  TB_TRY(io.h2d(WS_POS_A, pos, sizeof(double) * 3 * n, &dpos));
-  TB_TRY(io.out_buf(WS_VAL_B, out, sizeof(double) * dof * n, &dout));
-  TB_TRY(eval_field_dev(f, tq, bc, (double *)dpos, n, (double *)dout, 0, nullptr, 0.0));
-  TB_TRY(io.d2h(out, dout, sizeof(double) * dof * n));
-  if (bc == TBSLAS_PERIODIC) TB_TRY(io.d2h(pos, dpos, sizeof(double) * 3 * n));  // wrapped in place
-  return io.finish();
+  if (mem == TBSLAS_MEM_DEVICE) return eval_field_dev(f, tq, bc, pos, n, out, 0, nullptr, 0.0);
+  PipeSpec sp;
+  sp.h_pos = pos;
+  sp.h_pos_b = (bc == TBSLAS_PERIODIC) ? pos : nullptr;  // wrapped in place
+  sp.h_val = out;
+  sp.val_dof = dof;
+  return run_host_pipeline(
+      ctx, sp, n, [](PipeBufs &, size_t) { return (int)TBSLAS_OK; },
+      [&](PipeBufs &B, size_t m) { return eval_field_dev(f, tq, bc, B.pos, m, B.val, 0, nullptr, 0.0); });
 }
 
 int tbslas_b200_eval(tbslas_tree *t, int bc, double *pos, size_t n, double *out, int32_t *leaf_idx,
@@ -485,17 +602,16 @@ int tbslas_b200_eval(tbslas_tree *t, int bc, double *pos, size_t n, double *out,
   if (!t) return TBSLAS_ERR_INVALID;
   tbslas_ctx *ctx = t->ctx;
   if (n && (!pos || !out)) return fail(ctx, TBSLAS_ERR_INVALID, "null buffer");
-  HostIO io{ctx, mem};
-  void *dpos, *dout, *dleaf = nullptr;
-  TB_TRY(io.h2d(WS_POS_A, pos, sizeof(double) * 3 * n, &dpos));
-  TB_TRY(io.out_buf(WS_VAL_B, out, sizeof(double) * t->dof * n, &dout));
-  if (leaf_idx) TB_TRY(io.out_buf(WS_LEAFOUT, leaf_idx, sizeof(int32_t) * n, &dleaf));
-  TB_TRY(eval_tree_dev(t, bc, (double *)dpos, n, EPI_STORE, (double *)dout, nullptr, 0.0,
-                       (int32_t *)dleaf));
-  TB_TRY(io.d2h(out, dout, sizeof(double) * t->dof * n));
-  if (leaf_idx) TB_TRY(io.d2h(leaf_idx, dleaf, sizeof(int32_t) * n));
-  if (bc == TBSLAS_PERIODIC) TB_TRY(io.d2h(pos, dpos, sizeof(double) * 3 * n));
-  return io.finish();
+  if (mem == TBSLAS_MEM_DEVICE) return eval_tree_dev(t, bc, pos, n, EPI_STORE, out, nullptr, 0.0, leaf_idx);
+  PipeSpec sp;
+  sp.h_pos = pos;
+  sp.h_pos_b = (bc == TBSLAS_PERIODIC) ? pos : nullptr;
+  sp.h_val = out;
+  sp.val_dof = t->dof;
+  sp.h_leaf = leaf_idx;
+  return run_host_pipeline(
+      ctx, sp, n, [](PipeBufs &, size_t) { return (int)TBSLAS_OK; },
+      [&](PipeBufs &B, size_t m) { return eval_tree_dev(t, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, B.leaf); });
 }
 
 int tbslas_b200_eval_set4(tbslas_tree *const trees[4], const double times[4], double tq, int bc,
@@ -531,21 +647,23 @@ int tbslas_b200_traj_rk2(const tbslas_field *f1, const tbslas_field *f2, int bc,
   }
   if (dof != 3) return fail(ctx, TBSLAS_ERR_INVALID, "velocity field must have dof 3 (got %d)", dof);
   if (nrk < 1 || (n && (!pos || !out_pos))) return fail(ctx, TBSLAS_ERR_INVALID, "bad argument");
-  HostIO io{ctx, mem};
-  void *xsol, *xtmp;
-  TB_TRY(io.out_buf(WS_POS_A, out_pos, sizeof(double) * 3 * n, &xsol));
-  TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * n, &xtmp));
-  // xsol = xinit (traj.inc:57-58)
-  {
-    StageScope sc(ctx, mem == TBSLAS_MEM_HOST ? ST_H2D : ST_COMBINE, (double)(24 * n), 0);
-    TB_CUDA(ctx, cudaMemcpyAsync(xsol, pos, sizeof(double) * 3 * n,
-                                 mem == TBSLAS_MEM_HOST ? cudaMemcpyHostToDevice
-                                                        : cudaMemcpyDeviceToDevice,
-                                 ctx->stream));
+  if (mem == TBSLAS_MEM_HOST) {
+    PipeSpec sp;
+    sp.h_pos = pos;
+    sp.h_pos_a = out_pos;
+    sp.need_tmp = true;
+    return run_host_pipeline(
+        ctx, sp, n,
+        [&](PipeBufs &B, size_t m) { return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk); },
+        [](PipeBufs &, size_t) { return (int)TBSLAS_OK; });
   }
-  TB_TRY(traj_rk2_dev(f1, f2, bc, (double *)xsol, (double *)xtmp, n, tinit, tfinal, nrk));
-  TB_TRY(io.d2h(out_pos, xsol, sizeof(double) * 3 * n));
-  return io.finish();
+  void *xtmp;
+  TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * n, &xtmp));
+  {  // xsol = xinit (traj.inc:57-58)
+    StageScope sc(ctx, ST_COMBINE, (double)(24 * n), 0);
+    TB_CUDA(ctx, cudaMemcpyAsync(out_pos, pos, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return traj_rk2_dev(f1, f2, bc, out_pos, (double *)xtmp, n, tinit, tfinal, nrk);
 }
 
 // pos == nullptr: the arrival points are generated on the device from `con`'s own leaves
@@ -570,6 +688,18 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
   if (nrk < 1 || (n && !out_vals)) return fail(ctx, TBSLAS_ERR_INVALID, "bad argument");
   const double tinit = timestep * dt;   // semilag.inc:34-35
   const double tfinal = tinit - dt;
+  if (mem == TBSLAS_MEM_HOST && !insitu) {
+    PipeSpec sp;
+    sp.h_pos = pos;
+    sp.h_pos_a = out_dep;  // as ComputeTrajRK2 returns them, before the scalar evaluation wraps them
+    sp.h_val = out_vals;
+    sp.val_dof = con->dof;
+    sp.need_tmp = true;
+    return run_host_pipeline(
+        ctx, sp, n,
+        [&](PipeBufs &B, size_t m) { return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk); },
+        [&](PipeBufs &B, size_t m) { return eval_tree_dev(con, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, nullptr); });
+  }
   HostIO io{ctx, mem};
   void *xsol, *xtmp, *dval;
   if (mem == TBSLAS_MEM_DEVICE && out_dep)
@@ -581,18 +711,11 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
   if (insitu) {
     if (n) TB_TRY(launch_grid_points(ctx, con, (double *)xsol));
   } else {
-    StageScope sc(ctx, mem == TBSLAS_MEM_HOST ? ST_H2D : ST_COMBINE, (double)(24 * n), 0);
-    TB_CUDA(ctx, cudaMemcpyAsync(xsol, pos, sizeof(double) * 3 * n,
-                                 mem == TBSLAS_MEM_HOST ? cudaMemcpyHostToDevice
-                                                        : cudaMemcpyDeviceToDevice,
-                                 ctx->stream));
+    StageScope sc(ctx, ST_COMBINE, (double)(24 * n), 0);
+    TB_CUDA(ctx, cudaMemcpyAsync(xsol, pos, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   TB_TRY(traj_rk2_dev(f1, f2, bc, (double *)xsol, (double *)xtmp, n, tinit, tfinal, nrk));
-  if (mem == TBSLAS_MEM_HOST && out_dep) {
-    // the departure points as ComputeTrajRK2 returns them, before the scalar evaluation
-    // wraps them (semilag.inc:40-43)
-    TB_TRY(io.d2h(out_dep, xsol, sizeof(double) * 3 * n));
-  } else if (mem == TBSLAS_MEM_DEVICE && out_dep && bc == TBSLAS_PERIODIC) {
+  if (mem == TBSLAS_MEM_DEVICE && out_dep && bc == TBSLAS_PERIODIC) {
     // keep the caller's departure points un-wrapped: evaluate on a copy
     TB_CUDA(ctx, cudaMemcpyAsync(xtmp, xsol, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice,
                                  ctx->stream));

@@ -51,7 +51,9 @@ enum Slot {
   WS_POS_C,
   WS_VAL_A,      // double [n*dof] (x4 for set4)
   WS_VAL_B,
+  WS_VAL_C,      // second value buffer of the host-call pipeline
   WS_LEAFOUT,    // int32 [n] staging for host leaf_idx
+  WS_LEAFOUT2,
   WS_GRID,       // cubic grid staging
   WS_SEND,       // exchange buffers
   WS_RECV,
@@ -94,6 +96,9 @@ struct tbslas_ctx {
   cudaStream_t comm_stream = nullptr;  // NCCL traffic that overlaps the insider evaluation
   cudaEvent_t ev_comm = nullptr, ev_counts = nullptr, ev_packed = nullptr;
   size_t last_sent = 0, last_recv = 0;  // outsiders of the most recent tree evaluation
+  // host-buffer calls: H2D / compute / D2H of consecutive chunks overlap on three streams
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_pipe[5][2] = {};  // [in, phaseA, pos_out, phaseB, out][buffer parity]
   // pinned host scratch for small device->host reads (exchange counts: [nranks][nranks])
   unsigned *h_counts = nullptr;
 };
