@@ -155,6 +155,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     from tbslas_b200 import workloads
+    if args.workload.lower() == "c4":
+        return run_reference_cubic(args)
     wl = workloads.make(args.workload, None, args.scale)
     pts, nl = sample_points(wl, args.cpu_leaves)
     rate, kind, cores, sec = cpu_run(wl, pts, args.steps, args.warmup)
@@ -173,6 +175,42 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+    return 0
+
+
+def run_reference_cubic(args):
+    """C4 on the host: the reference's fast_interp (serial loop) on a bounded sample."""
+    import torch
+    from oracle import Oracle, have_ref
+    n_reg, dof = max(8, 256 >> args.scale), 3
+    grid, pts = cubic_workload(torch.device("cpu"), n_reg, dof)
+    kind = "reference" if have_ref() else "port"
+    orc = Oracle("ref" if kind == "reference" else "port")
+    n = pts.shape[0]
+    m = min(n, 1 << 21)
+    sp = pts.numpy()[:: max(1, n // m)][:m].copy()
+    g = grid.numpy()
+    ts = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        orc.fast_interp(g, dof, n_reg, sp)
+        if it >= args.warmup:
+            ts.append(time.perf_counter() - t0)
+    sec = float(np.mean(ts))
+    rate = sp.shape[0] / sec
+    print(json.dumps({
+        "impl": "reference", "metric": "departure-point evals/sec", "value": rate, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "c4: Taylor-Green velocity, uniform cubic-grid interpolation (fast_interp), "
+                               "%d^3 nodes x dof %d" % (n_reg, dof), "points_total": n,
+                   "sample": "%d strided query points per step" % sp.shape[0]},
+        "cpu_baseline": {"value": rate, "unit": "points/s", "cores": 1, "kind": kind,
+                         "sample": "fast_interp on %d strided query points; the reference's loop is serial "
+                                   "(tree_functor.h:106)" % sp.shape[0]},
+        "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
     return 0
 
 
@@ -357,6 +395,99 @@ def run_b200(args):
     return 0
 
 
+# --------------------------------------------------------------------------- C4: cubic grid
+def cubic_workload(dev, n_reg=256, dof=3, dt=0.0628 / 4):
+    """BASELINE config 4: Taylor-Green velocity sampled on a node-centred n_reg^3 grid,
+    queries = the grid nodes displaced by -dt*v (one backward Euler step)."""
+    import torch
+    x = torch.linspace(0.0, 1.0, n_reg, dtype=torch.float64, device=dev)
+    Z, Y, X = torch.meshgrid(x, x, x, indexing="ij")
+    a, b, c = 2 * np.pi * X, 2 * np.pi * Y, 2 * np.pi * Z
+    v = torch.stack([torch.cos(a) * torch.sin(b) * torch.sin(c),
+                     torch.sin(a) * torch.cos(b) * torch.sin(c),
+                     torch.sin(a) * torch.sin(b) * torch.cos(c)])[:dof].contiguous()  # [dof][z][y][x]
+    pts = torch.stack([X, Y, Z], dim=-1).reshape(-1, 3) - dt * v.reshape(dof, -1).t()[:, :3]
+    return v, pts.contiguous()
+
+
+def run_b200_cubic(args):
+    import torch
+    from tbslas_b200 import api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    n_reg, dof = max(8, 256 >> args.scale), 3
+    grid, pts = cubic_workload(dev, n_reg, dof)
+    n = pts.shape[0]
+    ctx = api.Context(0)
+    ctx.set_stream(torch.cuda.current_stream())
+    out = torch.empty((n, dof), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.fast_interp(grid, dof, n_reg, pts, out=out)
+        e1.record()
+        return e0, e1
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches0 = ctx.kernel_launches()
+    sampler.mark_begin()
+    evs = [step() for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    sampler.mark_end()
+    clocks = sampler.stop()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    launches = ctx.kernel_launches() - launches0
+    # end to end: pinned host buffers, grid + points in, values out
+    h_grid = torch.empty(grid.shape, dtype=torch.float64, pin_memory=True).copy_(grid)
+    h_pts = torch.empty(pts.shape, dtype=torch.float64, pin_memory=True).copy_(pts)
+    ctx.fast_interp(h_grid.numpy(), dof, n_reg, h_pts.numpy())
+    t0 = time.perf_counter()
+    hv = ctx.fast_interp(h_grid.numpy(), dof, n_reg, h_pts.numpy())
+    e2e_s = time.perf_counter() - t0
+    hbm_peak, hbm_src = load_peaks()
+    bytes_alg = n * (24 + 8 * dof + 8 * dof)
+    ach = bytes_alg / (ms * 1e-3) * 1e-9
+    line = {
+        "metric": "departure-point evals/sec", "value": n / (ms * 1e-3), "unit": "points/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "c4: Taylor-Green velocity, uniform cubic-grid interpolation (fast_interp), "
+                               "%d^3 nodes x dof %d" % (n_reg, dof), "points_total": n,
+                   "l2_policy": "256 MB written between timed iterations (L2 flush); grid is %.0f MB" %
+                                (grid.numel() * 8 / 1e6)},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": n / e2e_s, "unit": "points/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(grid.numel() * 8 + n * 24), "d2h_bytes_per_step": int(n * dof * 8),
+                "checksum": float(hv.sum())},
+        "roofline": {"bound": "hbm", "kernel": "cubic_grid_kernel", "achieved": ach, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src, "traffic": None,
+                     "bytes_model": "24 (xyz) + 8*dof (out) + 8*dof (each grid node once), SURVEY 8(d)",
+                     "avg_launch_ms": ms, "launches": args.steps},
+    }
+    if not args.no_cpu:
+        from oracle import Oracle, have_ref
+        kind = "reference" if have_ref() else "port"
+        orc = Oracle("ref" if kind == "reference" else "port")
+        m = min(n, 1 << 21)
+        sp = h_pts.numpy()[:: max(1, n // m)][:m].copy()
+        g = h_grid.numpy()
+        t0 = time.perf_counter()
+        orc.fast_interp(g, dof, n_reg, sp)
+        sec = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sp.shape[0] / sec, "unit": "points/s", "cores": 1, "kind": kind,
+                                "sample": "fast_interp on %d strided query points (%.1f s); the reference's loop "
+                                          "is serial (tree_functor.h:106)" % (sp.shape[0], sec)}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -371,6 +502,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    if args.workload.lower() == "c4" and args.impl == "b200":
+        sys.exit(run_b200_cubic(args))
     sys.exit(run_reference(args) if args.impl == "reference" else run_b200(args))
 
 

@@ -123,9 +123,10 @@ class Context:
         return Tree(self, ft.q, ft.dof, ft.coord, ft.depth, ft.coeff)
 
     # -- cubic grid (tbslas::fast_interp) ----------------------------------
-    def fast_interp(self, grid, dof: int, n_reg: int, pts):
+    def fast_interp(self, grid, dof: int, n_reg: int, pts, out=None):
         n = pts.shape[0]
-        out = _like(pts, (n, dof))
+        if out is None:
+            out = _like(pts, (n, dof))
         ga, gm = _addr(grid)
         pa, pm = _addr(pts)
         oa, _ = _addr(out)

@@ -104,20 +104,20 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
     return fail(ctx, TBSLAS_ERR_INVALID, "n = %zu exceeds the 32-bit point index range", n);
   if (epilogue == EPI_AXPY && t->dof != 3)
     return fail(ctx, TBSLAS_ERR_INVALID, "position update needs a dof-3 field (dof = %d)", t->dof);
-  const int tile_pts = eval_tile_points(t->q);
+  const int tile_pts = eval_tile_points(t);
   if (tile_pts <= 0)
     return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "Chebyshev degree %d not supported (1..%d)", t->q,
                 TBSLAS_MAX_CHEB_DEG);
   const size_t max_tiles = n / tile_pts + t->n_leaf + 2;
-  void *leaf, *rank, *count, *bin_start, *tile_start, *tile_map, *perm, *send_count = nullptr;
+  void *leaf, *rank, *count, *bin_start, *tile_start, *tile_map = nullptr, *perm, *send_count = nullptr;
   void *send_pos = nullptr, *send_idx = nullptr;
   TB_TRY(ws_get(ctx, WS_LEAF, sizeof(int32_t) * (n + 1), &leaf));
   TB_TRY(ws_get(ctx, WS_RANK, sizeof(uint32_t) * (n + 1), &rank));
   TB_TRY(ws_get(ctx, WS_PERM, sizeof(uint32_t) * (n + 1), &perm));
-  TB_TRY(ws_get(ctx, WS_COUNT, sizeof(uint32_t) * (t->n_leaf + 2 + kMaxRanks), &count));
+  TB_TRY(ws_get(ctx, WS_COUNT, sizeof(uint32_t) * (t->n_leaf + 2 + kMaxRanks + 1), &count));
   TB_TRY(ws_get(ctx, WS_BINSTART, sizeof(uint32_t) * (t->n_leaf + 2), &bin_start));
   TB_TRY(ws_get(ctx, WS_TILESTART, sizeof(uint32_t) * (t->n_leaf + 2), &tile_start));
-  TB_TRY(ws_get(ctx, WS_TILELEAF, sizeof(int2) * max_tiles, &tile_map));
+  if (eval_needs_tile_map(t)) TB_TRY(ws_get(ctx, WS_TILELEAF, sizeof(int2) * max_tiles, &tile_map));
   const bool multi = allow_exchange && ctx->nranks > 1;
   if (multi) {
     send_count = (uint32_t *)count + t->n_leaf + 2;
@@ -170,6 +170,7 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   ea.tile_map = (const int2 *)tile_map;
   ea.max_tiles = max_tiles;
   ea.epilogue = epilogue;
+  ea.chunk_counter = (unsigned *)count + t->n_leaf + 2 + kMaxRanks;
   ea.out = out;
   ea.base = base;
   ea.alpha = alpha;

@@ -1,25 +1,23 @@
-// Degree dispatch for the Chebyshev evaluation kernel: one fully unrolled
-// instantiation per degree 1..14 (compiled in cheb_eval_inst_*.cu), the degree-generic
-// kernel (cheb_eval_generic.cu) for 15..TBSLAS_MAX_CHEB_DEG.
+// Degree dispatch for the Chebyshev evaluation: the persistent warp-pipelined kernel
+// (cheb_eval_wt.cuh, one fully unrolled instantiation per degree 1..14, compiled in
+// cheb_eval_inst_*.cu) whenever one coefficient buffer per warp fits in shared memory at two
+// CTAs per SM; otherwise -- degrees 15..TBSLAS_MAX_CHEB_DEG, or very wide dof -- the
+// degree-generic kernel (cheb_eval_generic.cu).
 #include <cstdlib>
 
-#include "cheb_eval.cuh"
+#include "cheb_eval_wt.cuh"
 
 namespace tb {
 
-#define TB_DECL(Q) extern template int launch_cheb_eval_q<Q, eval_ppt(Q)>(tbslas_ctx *, const EvalArgs &);
+#define TB_DECL(Q) extern template int launch_cheb_eval_wt<Q, eval_ppt(Q)>(tbslas_ctx *, const EvalArgs &);
 TB_DECL(1) TB_DECL(2) TB_DECL(3) TB_DECL(4) TB_DECL(5) TB_DECL(6) TB_DECL(7) TB_DECL(8)
 TB_DECL(9) TB_DECL(10) TB_DECL(11) TB_DECL(12) TB_DECL(13) TB_DECL(14)
 #undef TB_DECL
-// experimental variants of the high-degree kernel (selected by TBSLAS_EVAL_VARIANT)
-extern template int launch_cheb_eval_q<14, 3, false>(tbslas_ctx *, const EvalArgs &);
-extern template int launch_cheb_eval_q<14, 4, true>(tbslas_ctx *, const EvalArgs &);
-extern template int launch_cheb_eval_q<14, 3, true>(tbslas_ctx *, const EvalArgs &);
-extern template int launch_cheb_eval_q<14, 2, false, 1, false>(tbslas_ctx *, const EvalArgs &);
-extern template int launch_cheb_eval_q<14, 2, false, 1, true>(tbslas_ctx *, const EvalArgs &);
-extern template int launch_cheb_eval_q<14, 2, false, 4, false>(tbslas_ctx *, const EvalArgs &);
+extern template int launch_cheb_eval_q<8, eval_ppt(8)>(tbslas_ctx *, const EvalArgs &);
+extern template int launch_cheb_eval_q<14, eval_ppt(14)>(tbslas_ctx *, const EvalArgs &);
 
 constexpr int kMaxUnrolledDeg = 14;  // beyond this nvcc stops unrolling: generic kernel
+constexpr size_t kWtSmemLimit = 27 * 1024;  // eight one-warp CTAs per SM must fit in 227 KB
 int launch_cheb_eval_generic(tbslas_ctx *ctx, const EvalArgs &a);
 
 static int eval_variant() {
@@ -31,33 +29,41 @@ static int eval_variant() {
   return v;
 }
 
-int eval_tile_points(int q) {
-  if (q < 1 || q > TBSLAS_MAX_CHEB_DEG) return 0;
-  if (q == 14 && eval_variant() == 1) return kEvalThreads * 3 * kEvalBatches;
-  if (q == 14 && eval_variant() == 2) return kEvalThreads * 4 * kEvalBatches;
-  if (q == 14 && eval_variant() == 3) return kEvalThreads * 3 * kEvalBatches;
-  if (q == 14 && (eval_variant() == 4 || eval_variant() == 5)) return kEvalThreads * 2;
-  return q <= kMaxUnrolledDeg ? kEvalThreads * eval_ppt(q) * kEvalBatches : kEvalThreads;
+// 0: warp-pipelined kernel, 1: one-tile-per-CTA kernel, 2: generic kernel
+static int eval_kind(int q, size_t stride) {
+  if (q < 1 || q > TBSLAS_MAX_CHEB_DEG) return -1;
+  if (q > kMaxUnrolledDeg) return 2;
+  if (eval_variant() == 1 && (q == 8 || q == 14)) return 1;
+  if (eval_variant() == 2) return 2;
+  const size_t smem = (stride + 11 * 32 * (size_t)eval_ppt(q) + 16) * sizeof(double);
+  return smem <= kWtSmemLimit ? 0 : 2;
 }
+
+int eval_tile_points(const tbslas_tree *t) {
+  switch (eval_kind(t->q, t->stride)) {
+    case 0: return 32 * eval_ppt(t->q);
+    case 1: return kEvalThreads * eval_ppt(t->q);
+    case 2: return kEvalThreads;
+    default: return 0;
+  }
+}
+
+bool eval_needs_tile_map(const tbslas_tree *t) { return eval_kind(t->q, t->stride) != 0; }
 
 int launch_cheb_eval(tbslas_ctx *ctx, const EvalArgs &a) {
   StageScope sc(ctx, ST_CHEB_EVAL, (double)a.n, 1);
-  if (a.tree->q == 14 && eval_variant() == 1) return launch_cheb_eval_q<14, 3, false>(ctx, a);
-  if (a.tree->q == 14 && eval_variant() == 2) return launch_cheb_eval_q<14, 4, true>(ctx, a);
-  if (a.tree->q == 14 && eval_variant() == 3) return launch_cheb_eval_q<14, 3, true>(ctx, a);
-  if (a.tree->q == 14 && eval_variant() == 4) return launch_cheb_eval_q<14, 2, false, 1, false>(ctx, a);
-  if (a.tree->q == 14 && eval_variant() == 5) return launch_cheb_eval_q<14, 2, false, 1, true>(ctx, a);
-  if (a.tree->q == 14 && eval_variant() == 6) return launch_cheb_eval_q<14, 2, false, 4, false>(ctx, a);
+  const int kind = eval_kind(a.tree->q, a.tree->stride);
+  if (kind == 2) return launch_cheb_eval_generic(ctx, a);
+  if (kind == 1)
+    return a.tree->q == 8 ? launch_cheb_eval_q<8, eval_ppt(8)>(ctx, a) : launch_cheb_eval_q<14, eval_ppt(14)>(ctx, a);
   switch (a.tree->q) {
 #define TB_CASE(Q) \
   case Q:          \
-    return launch_cheb_eval_q<Q, eval_ppt(Q)>(ctx, a);
+    return launch_cheb_eval_wt<Q, eval_ppt(Q)>(ctx, a);
     TB_CASE(1) TB_CASE(2) TB_CASE(3) TB_CASE(4) TB_CASE(5) TB_CASE(6) TB_CASE(7) TB_CASE(8)
     TB_CASE(9) TB_CASE(10) TB_CASE(11) TB_CASE(12) TB_CASE(13) TB_CASE(14)
 #undef TB_CASE
     default:
-      if (a.tree->q > kMaxUnrolledDeg && a.tree->q <= TBSLAS_MAX_CHEB_DEG)
-        return launch_cheb_eval_generic(ctx, a);
       return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "Chebyshev degree %d not supported", a.tree->q);
   }
 }

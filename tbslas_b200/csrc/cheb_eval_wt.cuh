@@ -1,0 +1,311 @@
+// Persistent, warp-pipelined variant of the Chebyshev evaluation kernel (degrees with a
+// fully unrolled contraction, q <= 14, and coefficient blocks small enough for one
+// buffer per warp).
+//
+// Same arithmetic as cheb_eval.cuh (ZLevel/RowPair, cheb_basis); what changes is the
+// scheduling around the contraction, which the ncu profile of the one-tile-per-CTA kernel
+// showed to cost ~8 % of the FP64 pipe (dependent gather perm -> pos -> bases at the head
+// of every CTA, hidden only by the one other CTA on the SM):
+//   * grid = 2 CTAs per SM, every WARP is an independent worker that walks a contiguous
+//     range of warp-tiles (32*PPT points of one leaf each; consecutive tiles mostly share
+//     the leaf);
+//   * the leaf's coefficient block lives in a per-warp shared-memory buffer, refilled by
+//     one bulk-TMA copy (mbarrier complete_tx) only when the leaf changes;
+//   * the gathers run two tiles ahead through cp.async: while tile t is contracted, the
+//     coordinates of tile t+1 (addresses from the already-landed slice of perm) and the
+//     perm slice of tile t+2 stream into shared memory, so no global-load latency is ever
+//     exposed in front of the FP64 work;
+//   * no tile map: a worker finds its first leaf by binary search in tile_start and walks
+//     forward.
+#pragma once
+#include "cheb_eval.cuh"
+
+namespace tb {
+
+__device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// per-worker staging area, in doubles: [3][TP] coordinates (SoA), [4] geom, 2 x [3][TP]
+// RK2 base positions (AXPY epilogue only), 3 x [TP] u32 perm slices (ring), 16 ints of
+// tile bookkeeping (kept in shared memory so that nothing but the bases and accumulators
+// is live in registers across the contraction)
+template <int PPT, int EPI>
+struct WarpStage {
+  static constexpr int TP = 32 * PPT;
+  static constexpr int kBase = (EPI == EPI_AXPY) ? 6 * TP : 0;
+  static constexpr int kPermDoubles = (3 * TP + 1) / 2;
+  static constexpr int kDoubles = 3 * TP + 4 + kBase + kPermDoubles + (kPermDoubles & 1) + 8;
+};
+// bookkeeping words
+enum {
+  CT_WL = 0, CT_TS, CT_TE, CT_BS, CT_BE,  // walker: current leaf, its tile and slot ranges
+  CT_RING = 5,                              // 3 x {leaf, slot0, cnt}; cnt == 0: end of stream
+  CT_N = 14,                                // stream index of the tile being contracted
+  CT_NEXT = 15,                             // next tile of the current chunk ...
+};
+// ... and its end live in the two ints that follow the 16 (the block is 8 doubles + 1)
+
+constexpr int kWtThreads = 32;  // one warp per CTA: every address below is CTA-uniform
+
+// Work distribution: tiles are handed out in chunks of `chunk` consecutive tiles from a
+// global counter (zeroed by the locate launcher), so a warp the scheduler favours simply
+// takes more chunks and all workers finish together.
+template <int Q, int PPT, int EPI>
+__global__ void __launch_bounds__(kWtThreads, 8)
+cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, unsigned chunk) {
+  constexpr int D = Q + 1;
+  constexpr int TP = 32 * PPT;
+  typedef WarpStage<PPT, EPI> Stage;
+  extern __shared__ __align__(128) double s_all[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_cend;
+  double *const s_coef = s_all;                       // [stride]
+  double *const s_x = s_all + p.stride;               // [3][TP]
+  double *const s_g = s_x + 3 * TP;                   // [4]
+  double *const s_b = s_g + 4;                        // [2][3][TP] (AXPY only)
+  uint32_t *const s_perm = reinterpret_cast<uint32_t *>(s_b + Stage::kBase);  // [3][TP]
+  int *const s_ctl = reinterpret_cast<int *>(s_x + Stage::kDoubles - 8);       // [16]
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    mbar_init(&s_bar, 1);
+    s_ctl[CT_N] = 0;
+    s_ctl[CT_NEXT] = 0;
+    s_cend = 0;
+  }
+  __syncwarp();
+  // lane 0 writes the descriptor of the next tile of the stream into ring slot n % 3
+  auto describe_next = [&](unsigned n) {
+    if (lane == 0) {
+      const unsigned n_tiles = __ldg(p.tile_start + p.n_bins);
+      unsigned t = (unsigned)s_ctl[CT_NEXT];
+      int *r = s_ctl + CT_RING + 3 * (n % 3);
+      bool have = true;
+      if (t >= (unsigned)s_cend) {  // take the next chunk
+        t = atomicAdd(chunk_counter, 1u) * chunk;
+        if (t >= n_tiles) {
+          have = false;
+          s_ctl[CT_NEXT] = (int)n_tiles;
+          s_cend = (int)n_tiles;
+        } else {
+          s_cend = (int)min(t + chunk, n_tiles);
+          // leaf of tile t = last bin j with tile_start[j] <= t
+          int lo = 0, hi = p.n_bins;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(p.tile_start + mid) <= t)
+              lo = mid;
+            else
+              hi = mid;
+          }
+          s_ctl[CT_WL] = lo;
+          s_ctl[CT_TS] = (int)__ldg(p.tile_start + lo);
+          s_ctl[CT_TE] = (int)__ldg(p.tile_start + lo + 1);
+          s_ctl[CT_BS] = (int)__ldg(p.bin_start + lo);
+          s_ctl[CT_BE] = (int)__ldg(p.bin_start + lo + 1);
+        }
+      }
+      if (have) {
+        int wl = s_ctl[CT_WL];
+        unsigned ts = (unsigned)s_ctl[CT_TS], te = (unsigned)s_ctl[CT_TE];
+        unsigned bs = (unsigned)s_ctl[CT_BS], be = (unsigned)s_ctl[CT_BE];
+        if (t >= te) {
+          do {
+            wl++;
+            ts = te;
+            te = __ldg(p.tile_start + wl + 1);
+            bs = be;
+            be = __ldg(p.bin_start + wl + 1);
+          } while (t >= te);
+          s_ctl[CT_WL] = wl;
+          s_ctl[CT_TS] = (int)ts;
+          s_ctl[CT_TE] = (int)te;
+          s_ctl[CT_BS] = (int)bs;
+          s_ctl[CT_BE] = (int)be;
+        }
+        const unsigned slot0 = bs + (t - ts) * TP;
+        r[0] = wl;
+        r[1] = (int)slot0;
+        r[2] = (int)min((unsigned)TP, be - slot0);
+        s_ctl[CT_NEXT] = (int)(t + 1);
+      } else {
+        r[0] = 0;
+        r[1] = 0;
+        r[2] = 0;
+      }
+    }
+    __syncwarp();
+  };
+  auto ring_cnt = [&](unsigned n) { return (unsigned)s_ctl[CT_RING + 3 * (n % 3) + 2]; };
+  auto fetch_perm = [&](unsigned n) {  // perm slice of stream tile n -> ring slot n % 3
+    const int *r = s_ctl + CT_RING + 3 * (n % 3);
+    const unsigned slot0 = (unsigned)r[1], cnt = (unsigned)r[2];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+      const unsigned o = s * 32 + lane;
+      cp_async_4(s_perm + (n % 3) * TP + o, p.perm + slot0 + (o < cnt ? o : 0u));
+    }
+  };
+  auto fetch_points = [&](unsigned n) {  // coordinates (+ RK2 base) + geom of tile n -> staging area
+    const int leaf = s_ctl[CT_RING + 3 * (n % 3)];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+      const unsigned o = s * 32 + lane;
+      const size_t i = s_perm[(n % 3) * TP + o];
+      const double *x = p.pos + 3 * i;
+      cp_async_8(s_x + o, x);
+      cp_async_8(s_x + TP + o, x + 1);
+      cp_async_8(s_x + 2 * TP + o, x + 2);
+      if (EPI == EPI_AXPY) {
+        const double *bp = p.base + 3 * i;
+        double *d = s_b + (n & 1) * 3 * TP + o;
+        cp_async_8(d, bp);
+        cp_async_8(d + TP, bp + 1);
+        cp_async_8(d + 2 * TP, bp + 2);
+      }
+    }
+    if (lane < 4) cp_async_8(s_g + lane, reinterpret_cast<const double *>(p.geom + leaf) + lane);
+  };
+
+  // ---- prologue: perm(0) -> wait -> points(0) + perm(1) in flight -------------------------
+  describe_next(0);
+  if (ring_cnt(0) == 0) return;
+  fetch_perm(0);
+  cp_async_wait_all();
+  __syncwarp();
+  fetch_points(0);
+  describe_next(1);
+  if (ring_cnt(1)) fetch_perm(1);
+  int cur_leaf = -1;
+  uint32_t phase = 0;
+
+#pragma unroll 1
+  for (;;) {
+    cp_async_wait_all();  // points(n), geom(n) and perm(n+1) have landed
+    __syncwarp();
+    double px[PPT][D], py[PPT][D], zc[PPT], z0[PPT];
+    {
+      const unsigned n = (unsigned)s_ctl[CT_N];
+      // ---- bases of tile n ------------------------------------------------------------
+      const double gx = s_g[0], gy = s_g[1], gz = s_g[2], gw = s_g[3];
+#pragma unroll
+      for (int s = 0; s < PPT; s++) {
+        const unsigned o = s * 32 + lane;
+        // xi = (x - c) * 2 * 2^depth - 1, left to right (tree_functor.h:288-293)
+        const double xi = __dadd_rn(__dmul_rn(__dsub_rn(s_x[o], gx), gw), -1.0);
+        const double yi = __dadd_rn(__dmul_rn(__dsub_rn(s_x[TP + o], gy), gw), -1.0);
+        const double zi = __dadd_rn(__dmul_rn(__dsub_rn(s_x[2 * TP + o], gz), gw), -1.0);
+        cheb_basis<Q>(xi, px[s]);
+        cheb_basis<Q>(yi, py[s]);
+        const bool inz = fabs(zi) <= 1.0;
+        zc[s] = inz ? zi : 0.0;
+        z0[s] = inz ? 1.0 : 0.0;
+      }
+      __syncwarp();  // every lane has consumed the staging area
+      // ---- keep two tiles in flight ----------------------------------------------------
+      if (ring_cnt(n + 1)) {
+        fetch_points(n + 1);
+        describe_next(n + 2);
+        if (ring_cnt(n + 2)) fetch_perm(n + 2);
+      }
+      // ---- coefficients of this leaf (only when the leaf changed) ------------------------
+      const int leaf0 = s_ctl[CT_RING + 3 * (n % 3)];
+      if (leaf0 != cur_leaf) {
+        cur_leaf = leaf0;
+        if (lane == 0) {
+          fence_proxy_async();  // earlier generic-proxy reads of the buffer vs. the async write
+          const uint32_t bytes = p.stride * 8u;
+          mbar_expect_tx(&s_bar, bytes);
+          tma_bulk_g2s(s_coef, p.coeff + (size_t)leaf0 * p.stride, bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+      }
+    }
+    // ---- contraction ------------------------------------------------------------------
+    bool last = false;
+#pragma unroll 1
+    for (int l = 0; l < p.dof; l++) {
+      const double2 *C2 = reinterpret_cast<const double2 *>(s_coef + l * p.ncoef_pad);
+      double u[PPT], tz0[PPT], tz1[PPT];
+#pragma unroll
+      for (int s = 0; s < PPT; s++) u[s] = tz0[s] = tz1[s] = 0.0;
+      ZLevel<Q, PPT, false, false, 0, 0>::run(C2, px, py, nullptr, zc, z0, tz0, tz1, u);
+      const unsigned n = (unsigned)s_ctl[CT_N];
+      const unsigned cnt0 = ring_cnt(n);
+#pragma unroll
+      for (int s = 0; s < PPT; s++) {
+        const unsigned o = s * 32 + lane;
+        if (o < cnt0) {
+          const size_t i = s_perm[(n % 3) * TP + o];
+          if (EPI == EPI_STORE) {
+            p.out[i * p.dof + l] = u[s];
+          } else {  // x' = x0 + alpha * v, multiply then add as traj.inc:36,42
+            p.out[3 * i + l] = __dadd_rn(s_b[(n & 1) * 3 * TP + l * TP + o], __dmul_rn(p.alpha, u[s]));
+          }
+        }
+      }
+      if (l + 1 == p.dof) {  // advance the stream
+        __syncwarp();        // all lanes are done with the coefficient buffer and the ring
+        last = ring_cnt(n + 1) == 0;
+        __syncwarp();
+        if (lane == 0) s_ctl[CT_N] = (int)(n + 1);
+      }
+    }
+    if (last) break;
+  }
+}
+
+template <int Q, int PPT, int EPI>
+size_t eval_wt_smem_bytes(const tbslas_tree *t) {
+  return (t->stride + (size_t)WarpStage<PPT, EPI>::kDoubles) * sizeof(double);
+}
+
+template <int Q, int PPT>
+int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
+  const tbslas_tree *t = a.tree;
+  EvalParams p;
+  p.coeff = t->d_coeff;
+  p.geom = t->d_geom;
+  p.stride = (unsigned)t->stride;
+  p.ncoef_pad = (unsigned)(t->stride / t->dof);
+  p.dof = t->dof;
+  p.n_bins = (int)t->n_leaf + 1;
+  p.pos = a.pos;
+  p.perm = a.perm;
+  p.bin_start = a.bin_start;
+  p.tile_start = a.tile_start;
+  p.tile_map = nullptr;
+  p.out = a.out;
+  p.base = a.base;
+  p.alpha = a.alpha;
+  // every CTA (one warp) is a worker: no more workers than tiles, at most 8 per SM
+  size_t grid = a.max_tiles;
+  if (grid > (size_t)8 * ctx->n_sm) grid = (size_t)8 * ctx->n_sm;
+  if (grid == 0) return TBSLAS_OK;
+  // chunks of consecutive tiles (leaf locality) small enough to balance the tail
+  size_t chunk = a.max_tiles / (grid * 16);
+  chunk = chunk < 1 ? 1 : (chunk > 16 ? 16 : chunk);
+  if (a.epilogue == EPI_STORE) {
+    const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_STORE>(t);
+    auto k = cheb_eval_wt_kernel<Q, PPT, EPI_STORE>;
+    if (smem > 48 * 1024)
+      TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk);
+  } else {
+    const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_AXPY>(t);
+    auto k = cheb_eval_wt_kernel<Q, PPT, EPI_AXPY>;
+    if (smem > 48 * 1024)
+      TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk);
+  }
+  TB_CUDA(ctx, cudaGetLastError());
+  return TBSLAS_OK;
+}
+
+}  // namespace tb

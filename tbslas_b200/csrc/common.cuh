@@ -154,7 +154,8 @@ struct LocateArgs {
   size_t n;
   int32_t *leaf;          // [n] local leaf index, n_leaf = null leaf, <= -2: outsider of rank -2-v
   uint32_t *rank;         // [n] position inside its leaf bin (or send bucket)
-  uint32_t *count;        // [n_leaf+2] zeroed by the launcher
+  uint32_t *count;        // [n_leaf+2 (+kMaxRanks) +1] zeroed by the launcher; the last word is
+                          // the evaluation kernel's chunk counter
   uint32_t *send_count;   // [nranks] (multi-rank only, zeroed by the launcher) or nullptr
 };
 int launch_locate(tbslas_ctx *ctx, const LocateArgs &a);
@@ -168,7 +169,7 @@ struct BinArgs {
   const uint32_t *count;
   uint32_t *bin_start;    // [n_leaf+2]
   uint32_t *tile_start;   // [n_leaf+2]; tile_start[n_leaf+1] = number of tiles
-  int2 *tile_map;         // [max_tiles] {leaf, first slot}
+  int2 *tile_map;         // [max_tiles] {leaf, first slot}; nullptr: not needed
   uint32_t *perm;         // [n] point ids grouped by leaf
   size_t max_tiles;
   // multi-rank only (send_count != nullptr): outsiders are packed into per-owner buckets
@@ -192,11 +193,13 @@ struct EvalArgs {
   const int2 *tile_map;
   size_t max_tiles;
   int epilogue;
+  unsigned *chunk_counter; // zeroed by launch_locate; work distribution of the persistent kernel
   double *out;             // STORE: [n][dof]; AXPY: [n][3] = base + alpha*value (dof must be 3)
   const double *base;
   double alpha;
 };
-int eval_tile_points(int q);  // points per tile the eval kernel for degree q consumes
+int eval_tile_points(const tbslas_tree *t);   // points per tile of the kernel that will run
+bool eval_needs_tile_map(const tbslas_tree *t);  // only the one-tile-per-CTA kernels index a tile map
 int launch_cheb_eval(tbslas_ctx *ctx, const EvalArgs &a);
 
 // combine.cu

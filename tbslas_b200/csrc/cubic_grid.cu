@@ -16,11 +16,16 @@ struct LagrDen {
   double d[4];
 };
 
+// DOF > 0: compile-time dof (accumulators in registers, each tap weight M0*M1M2 formed once
+// and shared by all components -- the same product the reference forms per component, so the
+// sums stay bit-identical); DOF == 0: runtime dof, one component at a time.
+template <int DOF>
 __global__ void __launch_bounds__(256)
-cubic_grid_kernel(const double *__restrict__ grid, int n_reg, int dof, const double *__restrict__ pos,
+cubic_grid_kernel(const double *__restrict__ grid, int n_reg, int dof_rt, const double *__restrict__ pos,
                   size_t n, double *__restrict__ out, LagrDen den) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int dof = DOF > 0 ? DOF : dof_rt;
   const double x[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
   if (x[0] < 0 || x[0] > 1.0 || x[1] < 0 || x[1] > 1.0 || x[2] < 0 || x[2] > 1.0) {
     for (int k = 0; k < dof; k++) out[i * dof + k] = 0;
@@ -46,21 +51,43 @@ cubic_grid_kernel(const double *__restrict__ grid, int n_reg, int dof, const dou
     }
   }
   const size_t n3 = (size_t)n_reg * n_reg * n_reg;
-  for (int k = 0; k < dof; k++) {
-    const double *gk = grid + k * n3;
-    double val = 0;
+  if (DOF > 0) {
+    double val[DOF > 0 ? DOF : 1];
+#pragma unroll
+    for (int k = 0; k < DOF; k++) val[k] = 0;
 #pragma unroll
     for (int j2 = 0; j2 < 4; j2++) {
 #pragma unroll
       for (int j1 = 0; j1 < 4; j1++) {
         const double m12 = __dmul_rn(M[1][j1], M[2][j2]);
-        const double *row = gk + (size_t)n_reg * ((g[1] + j1) + (size_t)n_reg * (g[2] + j2)) + g[0];
+        const double *row = grid + (size_t)n_reg * ((g[1] + j1) + (size_t)n_reg * (g[2] + j2)) + g[0];
 #pragma unroll
-        for (int j0 = 0; j0 < 4; j0++)
-          val = __dadd_rn(val, __dmul_rn(__dmul_rn(M[0][j0], m12), __ldg(row + j0)));
+        for (int j0 = 0; j0 < 4; j0++) {
+          const double w = __dmul_rn(M[0][j0], m12);
+#pragma unroll
+          for (int k = 0; k < DOF; k++) val[k] = __dadd_rn(val[k], __dmul_rn(w, __ldg(row + k * n3 + j0)));
+        }
       }
     }
-    out[i * dof + k] = val;
+#pragma unroll
+    for (int k = 0; k < DOF; k++) out[i * DOF + k] = val[k];
+  } else {
+    for (int k = 0; k < dof; k++) {
+      const double *gk = grid + k * n3;
+      double val = 0;
+#pragma unroll
+      for (int j2 = 0; j2 < 4; j2++) {
+#pragma unroll
+        for (int j1 = 0; j1 < 4; j1++) {
+          const double m12 = __dmul_rn(M[1][j1], M[2][j2]);
+          const double *row = gk + (size_t)n_reg * ((g[1] + j1) + (size_t)n_reg * (g[2] + j2)) + g[0];
+#pragma unroll
+          for (int j0 = 0; j0 < 4; j0++)
+            val = __dadd_rn(val, __dmul_rn(__dmul_rn(M[0][j0], m12), __ldg(row + j0)));
+        }
+      }
+      out[i * dof + k] = val;
+    }
   }
 }
 
@@ -75,8 +102,13 @@ int launch_cubic_grid(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, c
       if (i != j) d = d / (double)(i - j);
     den.d[i] = d;
   }
-  cubic_grid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(grid, n_reg, dof, pos, n,
-                                                                         out, den);
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  switch (dof) {
+    case 1: cubic_grid_kernel<1><<<nb, 256, 0, ctx->stream>>>(grid, n_reg, dof, pos, n, out, den); break;
+    case 2: cubic_grid_kernel<2><<<nb, 256, 0, ctx->stream>>>(grid, n_reg, dof, pos, n, out, den); break;
+    case 3: cubic_grid_kernel<3><<<nb, 256, 0, ctx->stream>>>(grid, n_reg, dof, pos, n, out, den); break;
+    default: cubic_grid_kernel<0><<<nb, 256, 0, ctx->stream>>>(grid, n_reg, dof, pos, n, out, den); break;
+  }
   TB_CUDA(ctx, cudaGetLastError());
   return TBSLAS_OK;
 }

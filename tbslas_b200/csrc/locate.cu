@@ -213,9 +213,7 @@ int launch_locate(tbslas_ctx *ctx, const LocateArgs &a) {
   const tbslas_tree *t = a.tree;
   StageScope sc(ctx, ST_LOCATE, (double)a.n, 1);
   const bool multi = ctx->nranks > 1 && a.send_count;
-  TB_CUDA(ctx, cudaMemsetAsync(a.count, 0,
-                               sizeof(uint32_t) * (t->n_leaf + 2 + (multi ? ctx->nranks : 0)),
-                               ctx->stream));
+  TB_CUDA(ctx, cudaMemsetAsync(a.count, 0, sizeof(uint32_t) * (t->n_leaf + 2 + kMaxRanks + 1), ctx->stream));
   if (a.n == 0) return TBSLAS_OK;
   const size_t per_cta = (size_t)kLocateThreads * kLocItems;
   const unsigned grid = (unsigned)((a.n + per_cta - 1) / per_cta);
@@ -353,14 +351,16 @@ __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint
 }
 
 int launch_bin(tbslas_ctx *ctx, const BinArgs &a) {
-  StageScope sc(ctx, ST_BIN, (double)a.n, 3);
+  StageScope sc(ctx, ST_BIN, (double)a.n, a.tile_map ? 3 : 2);
   const int n_bins = (int)a.n_leaf + 1;  // + null leaf
   scan_bins_kernel<<<1, kScanThreads, 0, ctx->stream>>>(a.count, n_bins, a.tile_pts, a.bin_start,
                                                         a.tile_start);
   TB_CUDA(ctx, cudaGetLastError());
-  tile_map_kernel<<<(unsigned)((a.max_tiles + 255) / 256), 256, 0, ctx->stream>>>(
-      a.bin_start, a.tile_start, n_bins, a.tile_pts, a.tile_map, (unsigned)a.max_tiles);
-  TB_CUDA(ctx, cudaGetLastError());
+  if (a.tile_map) {
+    tile_map_kernel<<<(unsigned)((a.max_tiles + 255) / 256), 256, 0, ctx->stream>>>(
+        a.bin_start, a.tile_start, n_bins, a.tile_pts, a.tile_map, (unsigned)a.max_tiles);
+    TB_CUDA(ctx, cudaGetLastError());
+  }
   if (a.n) {
     const unsigned grid = (unsigned)((a.n + 255) / 256);
     if (a.send_count)
