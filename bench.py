@@ -216,6 +216,8 @@ def run_reference_cubic(args):
 
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from tbslas_b200 import api, workloads
@@ -242,11 +244,12 @@ def run_b200(args):
         first = workloads.partition_leaves(wl.con.n_leaf, world)
         splitters = wl.con.keys()[first[:-1]]
         con_local = wl.con.shard(int(first[rank]), int(first[rank + 1]))
-        vel_local = [workloads.shard_by_splitters(v, splitters, rank) for v in wl.vel]
+        vel_local = wl.vel if args.replicate_velocity else \
+            [workloads.shard_by_splitters(v, splitters, rank) for v in wl.vel]
     else:
         con_local, vel_local = wl.con, wl.vel
     tcon = ctx.tree(con_local)
-    tvel = [ctx.tree(v) for v in vel_local]
+    tvel = [ctx.tree(v, replicated=(world > 1 and args.replicate_velocity)) for v in vel_local]
     con_f = api.NodeFieldFunctor(tcon)
     vel_f = api.NodeFieldFunctor(tvel[0]) if len(tvel) == 1 else api.FieldSetFunctor(tvel, wl.vel_times)
 
@@ -292,10 +295,17 @@ def run_b200(args):
     launches = ctx.kernel_launches() - launches0
     prof = ctx.profile()
     ctx.profile_enable(False)
+    per_rank = None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        mine = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["ms"] > 0}
+        mine["points"] = n_local
+        mine["sent_last_eval"], mine["received_last_eval"] = exch
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
@@ -369,7 +379,9 @@ def run_b200(args):
                                 (n_local * 24 / 1e9),
                    "partition": "single GPU" if world == 1 else
                                 "equal-count contiguous Morton ranges of the advected tree; velocity "
-                                "tree re-partitioned with the same break points (whole leaves)",
+                                + ("tree replicated on every rank (no exchange for velocity evaluations)"
+                                   if args.replicate_velocity else
+                                   "tree re-partitioned with the same break points (whole leaves)"),
                    "exchange": None if world == 1 else
                    {"collective": "NCCL all-to-all-v (grouped send/recv), forward xyz + reverse values",
                     "rank0_last_eval_sent": exch[0], "rank0_last_eval_received": exch[1]}},
@@ -379,6 +391,8 @@ def run_b200(args):
                 "steps": e2e_steps, "checksum": checksum},
         "roofline": roofline,
     }
+    if per_rank is not None:
+        line["per_rank_stage_ms"] = per_rank
     if world == 1 and not args.no_cpu:
         pts, nl = sample_points(wl, args.cpu_leaves)
         rate, kind, cores, sec = cpu_run(wl, pts, 1, 1)
@@ -499,6 +513,8 @@ def main():
     ap.add_argument("--cpu-leaves", type=int, default=1024,
                     help="leaves in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--replicate-velocity", action="store_true",
+                    help="multi-GPU: every rank holds the whole velocity tree (SURVEY 8(f) row f3)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

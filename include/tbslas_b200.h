@@ -109,6 +109,15 @@ int tbslas_b200_comm_last_exchange(tbslas_ctx *ctx, size_t *sent, size_t *receiv
 int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf,
                             const double *coord, const uint8_t *depth,
                             const double *coeff, int mem, tbslas_tree **tree);
+/* The same, for a tree that every rank of a multi-rank context holds IN FULL (the caller
+ * passes all leaves on every rank): evaluations on it are local and not collective -- no
+ * point exchange.  The reference has no such mode (an MPI rank only ever holds its own
+ * range); it is the "replicate instead of exchange" option for trees that are small next
+ * to 180 GB of HBM, e.g. a smooth velocity field.  Identical to tree_create in a
+ * single-rank context. */
+int tbslas_b200_tree_create_replicated(tbslas_ctx *ctx, int q, int dof, size_t n_leaf,
+                                       const double *coord, const uint8_t *depth,
+                                       const double *coeff, int mem, tbslas_tree **tree);
 /* New coefficients on the same leaves (what SetTreeGridValues writes every step,
  * tree_utils.h:547-550). */
 int tbslas_b200_tree_update_coeff(tbslas_tree *tree, const double *coeff, int mem);

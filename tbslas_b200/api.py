@@ -119,8 +119,10 @@ class Context:
         return r.value, n.value
 
     # -- trees --------------------------------------------------------------
-    def tree(self, ft: FlatTree) -> "Tree":
-        return Tree(self, ft.q, ft.dof, ft.coord, ft.depth, ft.coeff)
+    def tree(self, ft: FlatTree, replicated: bool = False) -> "Tree":
+        """replicated=True (multi-rank contexts): ``ft`` is the WHOLE tree on every rank and
+        evaluations on it never exchange points (tbslas_b200_tree_create_replicated)."""
+        return Tree(self, ft.q, ft.dof, ft.coord, ft.depth, ft.coeff, replicated)
 
     # -- cubic grid (tbslas::fast_interp) ----------------------------------
     def fast_interp(self, grid, dof: int, n_reg: int, pts, out=None):
@@ -163,14 +165,15 @@ class Context:
 class Tree:
     """Device-resident leaf list of one Chebyshev octree (tbslas_b200_tree_create)."""
 
-    def __init__(self, ctx: Context, q, dof, coord, depth, coeff):
+    def __init__(self, ctx: Context, q, dof, coord, depth, coeff, replicated: bool = False):
         self.ctx, self.q, self.dof = ctx, int(q), int(dof)
         coord = np.ascontiguousarray(coord, dtype=np.float64)
         depth = np.ascontiguousarray(depth, dtype=np.uint8)
         coeff = np.ascontiguousarray(coeff, dtype=np.float64)
         self.n_leaf = coord.shape[0]
         h = C.c_void_p()
-        ctx.check(ctx.lib.tbslas_b200_tree_create(ctx.h, self.q, self.dof, self.n_leaf,
+        create = ctx.lib.tbslas_b200_tree_create_replicated if replicated else ctx.lib.tbslas_b200_tree_create
+        ctx.check(create(ctx.h, self.q, self.dof, self.n_leaf,
                                                   coord.ctypes.data, depth.ctypes.data,
                                                   coeff.ctypes.data, MEM_HOST, C.byref(h)))
         self.h = h

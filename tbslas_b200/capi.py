@@ -24,7 +24,7 @@ SYMBOLS = [
     "tbslas_b200_synchronize", "tbslas_b200_last_error", "tbslas_b200_version",
     "tbslas_b200_comm_unique_id", "tbslas_b200_comm_init", "tbslas_b200_comm_rank",
     "tbslas_b200_comm_last_exchange",
-    "tbslas_b200_tree_create", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_destroy",
+    "tbslas_b200_tree_create", "tbslas_b200_tree_create_replicated", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_destroy",
     "tbslas_b200_tree_info", "tbslas_b200_eval", "tbslas_b200_eval_set4",
     "tbslas_b200_eval_extrap", "tbslas_b200_eval_field", "tbslas_b200_traj_rk2",
     "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_cubic_eval", "tbslas_b200_collect_grid_points",
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
     L.tbslas_b200_comm_last_exchange.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
     L.tbslas_b200_tree_create.argtypes = [vp, C.c_int, C.c_int, sz, dp, vp, dp, C.c_int,
                                           C.POINTER(vp)]
+    L.tbslas_b200_tree_create_replicated.argtypes = L.tbslas_b200_tree_create.argtypes
     L.tbslas_b200_tree_update_coeff.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_tree_destroy.argtypes = [vp]
     L.tbslas_b200_tree_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int),

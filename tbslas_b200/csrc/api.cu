@@ -88,9 +88,9 @@ static const char *kStageNames[ST_COUNT] = {"H2D",     "D2H",       "Locate", "B
 // multi-rank pieces (comm.cu)
 int comm_tree_splitters(tbslas_tree *t, uint64_t first_key);
 int comm_begin_exchange(tbslas_ctx *ctx, const uint32_t *send_count_dev);
-int comm_finish_exchange(tbslas_tree *t, int bc, const double *send_pos, const uint32_t *send_idx,
-                         int epilogue, double *out, const double *base, double alpha,
-                         int32_t *leaf_out);
+int comm_forward_exchange(tbslas_tree *t, const double *send_pos, bool want_leaf);
+int comm_finish_exchange(tbslas_tree *t, int bc, const uint32_t *send_idx, int epilogue, double *out,
+                         const double *base, double alpha, int32_t *leaf_out);
 void comm_destroy(tbslas_ctx *ctx);
 
 // ---------------------------------------------------------------------------
@@ -118,7 +118,7 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   TB_TRY(ws_get(ctx, WS_BINSTART, sizeof(uint32_t) * (t->n_leaf + 2), &bin_start));
   TB_TRY(ws_get(ctx, WS_TILESTART, sizeof(uint32_t) * (t->n_leaf + 2), &tile_start));
   if (eval_needs_tile_map(t)) TB_TRY(ws_get(ctx, WS_TILELEAF, sizeof(int2) * max_tiles, &tile_map));
-  const bool multi = allow_exchange && ctx->nranks > 1;
+  const bool multi = allow_exchange && ctx->nranks > 1 && !t->replicated;
   if (multi) {
     send_count = (uint32_t *)count + t->n_leaf + 2;
     // worst case: every point is an outsider (sizes must be known before the counts are)
@@ -158,7 +158,14 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
     ba.send_idx = (uint32_t *)send_idx;
   }
   TB_TRY(launch_bin(ctx, ba));
-  if (multi) TB_CUDA(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+  // The persistent evaluation kernel fills every SM, so an NCCL kernel enqueued behind it on
+  // another stream could not start before it drains; posting the forward exchange FIRST lets the
+  // outsiders travel while the insiders are evaluated (TBSLAS_EXCHANGE_FIRST=0: old order).
+  static const bool exchange_first = !(getenv("TBSLAS_EXCHANGE_FIRST") && atoi(getenv("TBSLAS_EXCHANGE_FIRST")) == 0);
+  if (multi) {
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+    if (exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
+  }
 
   EvalArgs ea;
   ea.tree = t;
@@ -181,9 +188,10 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
                                  ctx->stream));
     TB_TRY(launch_leaf_fixup(ctx, leaf_out, n, t->n_leaf, t->leaf_offset));
   }
-  if (multi)
-    TB_TRY(comm_finish_exchange(t, bc, (const double *)send_pos, (const uint32_t *)send_idx, epilogue,
-                                out, base, alpha, leaf_out));
+  if (multi) {
+    if (!exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
+    TB_TRY(comm_finish_exchange(t, bc, (const uint32_t *)send_idx, epilogue, out, base, alpha, leaf_out));
+  }
   return TBSLAS_OK;
 }
 
@@ -471,15 +479,31 @@ int tbslas_b200_synchronize(tbslas_ctx *ctx) {
 const char *tbslas_b200_last_error(tbslas_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 // ---------------------------------------------------------------- trees
+static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, const double *coord,
+                            const uint8_t *depth, const double *coeff, int mem, bool replicated,
+                            tbslas_tree **out);
+
 int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, const double *coord,
                             const uint8_t *depth, const double *coeff, int mem, tbslas_tree **out) {
+  return tree_create_impl(ctx, q, dof, n_leaf, coord, depth, coeff, mem, false, out);
+}
+
+int tbslas_b200_tree_create_replicated(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, const double *coord,
+                                       const uint8_t *depth, const double *coeff, int mem,
+                                       tbslas_tree **out) {
+  return tree_create_impl(ctx, q, dof, n_leaf, coord, depth, coeff, mem, true, out);
+}
+
+static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, const double *coord,
+                            const uint8_t *depth, const double *coeff, int mem, bool replicated,
+                            tbslas_tree **out) {
   if (!ctx || !out) return TBSLAS_ERR_INVALID;
   *out = nullptr;
   if (q < 1 || q > TBSLAS_MAX_CHEB_DEG)
     return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "Chebyshev degree %d not supported (1..%d)", q,
                 TBSLAS_MAX_CHEB_DEG);
   // a rank of a multi-rank context may own no leaf of this tree (empty Morton range)
-  const size_t min_leaf = ctx->nranks > 1 ? 0 : 1;
+  const size_t min_leaf = (ctx->nranks > 1 && !replicated) ? 0 : 1;
   if (dof < 1 || dof > 16 || n_leaf < min_leaf || n_leaf > 0x7ffffff0u ||
       (n_leaf && (!coord || !depth || !coeff)))
     return fail(ctx, TBSLAS_ERR_INVALID, "tree_create: bad argument (dof=%d, n_leaf=%zu)", dof, n_leaf);
@@ -511,6 +535,7 @@ int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   t->q = q;
   t->dof = dof;
   t->n_leaf = n_leaf;
+  t->replicated = replicated;
   t->ncoef = (size_t)(q + 1) * (q + 2) * (q + 3) / 6;
   const size_t ncoef_pad = t->ncoef + (t->ncoef & 1);  // 16-byte rows for TMA / LDS.128
   t->stride = ncoef_pad * dof;
@@ -536,7 +561,7 @@ int tbslas_b200_tree_create(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   t->splitters.assign(1, n_leaf ? hk[0] : ~0ull);
   int rc = n_leaf ? tbslas_b200_tree_update_coeff(t, coeff, mem) : TBSLAS_OK;
   if (rc != TBSLAS_OK) return bail(rc);
-  if (ctx->nranks > 1) {
+  if (ctx->nranks > 1 && !replicated) {
     rc = comm_tree_splitters(t, n_leaf ? hk[0] : ~0ull);
     if (rc != TBSLAS_OK) return bail(rc);
   }

@@ -194,58 +194,71 @@ int comm_begin_exchange(tbslas_ctx *ctx, const uint32_t *send_count_dev) {
   return TBSLAS_OK;
 }
 
-// Step 2 (after the insider evaluation has been enqueued; `ev_packed` was recorded on the
-// main stream after the pack): forward exchange, evaluation of what arrived, reverse
-// exchange, unpack.
-int comm_finish_exchange(tbslas_tree *t, int bc, const double *send_pos, const uint32_t *send_idx,
-                         int epilogue, double *out, const double *base, double alpha,
-                         int32_t *leaf_out) {
-  tbslas_ctx *ctx = t->ctx;
-  const int np = ctx->nranks, me = ctx->rank;
-  TB_CUDA(ctx, cudaEventSynchronize(ctx->ev_counts));
+// Step 2: the host learns the count matrix (one sync), sizes the receive buffers and posts the
+// forward exchange (3 doubles per outsider, OutScatterForward) on the comm stream behind the
+// pack (`ev_packed` was recorded on the main stream after it).
+struct ExchangeState {
   unsigned send_cnt[kMaxRanks], recv_cnt[kMaxRanks];
   size_t n_send = 0, n_recv = 0;
+  void *recv_pos = nullptr, *recv_val = nullptr, *ret_val = nullptr, *recv_leaf = nullptr, *ret_leaf = nullptr;
+};
+static ExchangeState g_xs;  // one exchange in flight per process (one context per GPU per process)
+
+int comm_forward_exchange(tbslas_tree *t, const double *send_pos, bool want_leaf) {
+  tbslas_ctx *ctx = t->ctx;
+  const int np = ctx->nranks, me = ctx->rank;
+  ExchangeState &x = g_xs;
+  TB_CUDA(ctx, cudaEventSynchronize(ctx->ev_counts));
+  x.n_send = x.n_recv = 0;
   for (int r = 0; r < np; r++) {
-    send_cnt[r] = ctx->h_counts[me * np + r];
-    recv_cnt[r] = ctx->h_counts[r * np + me];
-    n_send += send_cnt[r];
-    n_recv += recv_cnt[r];
+    x.send_cnt[r] = ctx->h_counts[me * np + r];
+    x.recv_cnt[r] = ctx->h_counts[r * np + me];
+    x.n_send += x.send_cnt[r];
+    x.n_recv += x.recv_cnt[r];
   }
-  if (send_cnt[me] || recv_cnt[me]) return fail(ctx, TBSLAS_ERR_COMM, "self-send in the count matrix");
-  ctx->last_sent = n_send;
-  ctx->last_recv = n_recv;
+  if (x.send_cnt[me] || x.recv_cnt[me]) return fail(ctx, TBSLAS_ERR_COMM, "self-send in the count matrix");
+  ctx->last_sent = x.n_send;
+  ctx->last_recv = x.n_recv;
   const int dof = t->dof;
-  void *recv_pos, *recv_val, *ret_val, *recv_leaf = nullptr, *ret_leaf = nullptr;
-  TB_TRY(ws_get(ctx, WS_RECV, sizeof(double) * 3 * (n_recv + 1), &recv_pos));
-  TB_TRY(ws_get(ctx, WS_SENDVAL, sizeof(double) * dof * (n_recv + 1), &recv_val));
-  TB_TRY(ws_get(ctx, WS_RECVVAL, sizeof(double) * dof * (n_send + 1), &ret_val));
-  if (leaf_out) {
-    TB_TRY(ws_get(ctx, WS_RECVLEAF, sizeof(int32_t) * (n_recv + 1), &recv_leaf));
-    TB_TRY(ws_get(ctx, WS_RETLEAF, sizeof(int32_t) * (n_send + 1), &ret_leaf));
+  TB_TRY(ws_get(ctx, WS_RECV, sizeof(double) * 3 * (x.n_recv + 1), &x.recv_pos));
+  TB_TRY(ws_get(ctx, WS_SENDVAL, sizeof(double) * dof * (x.n_recv + 1), &x.recv_val));
+  TB_TRY(ws_get(ctx, WS_RECVVAL, sizeof(double) * dof * (x.n_send + 1), &x.ret_val));
+  x.recv_leaf = x.ret_leaf = nullptr;
+  if (want_leaf) {
+    TB_TRY(ws_get(ctx, WS_RECVLEAF, sizeof(int32_t) * (x.n_recv + 1), &x.recv_leaf));
+    TB_TRY(ws_get(ctx, WS_RETLEAF, sizeof(int32_t) * (x.n_send + 1), &x.ret_leaf));
   }
-  {  // forward: 3 doubles per outsider (OutScatterForward), overlapping the insider evaluation
-    StageScope sc(ctx, ST_EXCHANGE, (double)(24 * (n_send + n_recv)), 0);
-    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
-    TB_TRY(alltoallv(ctx, send_pos, send_cnt, recv_pos, recv_cnt, 24, ctx->comm_stream));
-    TB_TRY(chain(ctx, ctx->comm_stream, ctx->stream));
-  }
+  StageScope sc(ctx, ST_EXCHANGE, (double)(24 * (x.n_send + x.n_recv)), 0);
+  TB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+  TB_TRY(alltoallv(ctx, send_pos, x.send_cnt, x.recv_pos, x.recv_cnt, 24, ctx->comm_stream));
+  TB_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+  return TBSLAS_OK;
+}
+
+// Step 3: evaluation of what arrived, reverse exchange, unpack.
+int comm_finish_exchange(tbslas_tree *t, int bc, const uint32_t *send_idx, int epilogue, double *out,
+                         const double *base, double alpha, int32_t *leaf_out) {
+  tbslas_ctx *ctx = t->ctx;
+  ExchangeState &x = g_xs;
+  const int dof = t->dof;
+  TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
   // OutEvaluation: every received point lies in this rank's Morton range
-  TB_TRY(eval_received_points(t, bc, (double *)recv_pos, n_recv, (double *)recv_val, (int32_t *)recv_leaf));
+  TB_TRY(eval_received_points(t, bc, (double *)x.recv_pos, x.n_recv, (double *)x.recv_val, (int32_t *)x.recv_leaf));
   {  // reverse: dof doubles per outsider (OutScatterReverse)
-    StageScope sc(ctx, ST_EXCHANGE, (double)(8 * dof * (n_send + n_recv)), 0);
-    TB_TRY(alltoallv(ctx, recv_val, recv_cnt, ret_val, send_cnt, 8 * (size_t)dof, ctx->stream));
-    if (leaf_out) TB_TRY(alltoallv(ctx, recv_leaf, recv_cnt, ret_leaf, send_cnt, 4, ctx->stream));
+    StageScope sc(ctx, ST_EXCHANGE, (double)(8 * dof * (x.n_send + x.n_recv)), 0);
+    TB_TRY(alltoallv(ctx, x.recv_val, x.recv_cnt, x.ret_val, x.send_cnt, 8 * (size_t)dof, ctx->stream));
+    if (leaf_out) TB_TRY(alltoallv(ctx, x.recv_leaf, x.recv_cnt, x.ret_leaf, x.send_cnt, 4, ctx->stream));
   }
-  if (n_send) {
-    StageScope sc(ctx, ST_UNPACK, (double)n_send, 1);
-    const size_t m = n_send * dof;
+  if (x.n_send) {
+    StageScope sc(ctx, ST_UNPACK, (double)x.n_send, 1);
+    const size_t m = x.n_send * dof;
     const unsigned grid = (unsigned)((m + 255) / 256);
     if (epilogue == EPI_STORE)
-      unpack_kernel<EPI_STORE><<<grid, 256, 0, ctx->stream>>>((const double *)ret_val, (const int32_t *)ret_leaf,
-                                                            send_idx, n_send, dof, out, base, alpha, leaf_out);
+      unpack_kernel<EPI_STORE><<<grid, 256, 0, ctx->stream>>>((const double *)x.ret_val, (const int32_t *)x.ret_leaf,
+                                                            send_idx, x.n_send, dof, out, base, alpha, leaf_out);
     else
-      unpack_kernel<EPI_AXPY><<<grid, 256, 0, ctx->stream>>>((const double *)ret_val, (const int32_t *)ret_leaf,
-                                                           send_idx, n_send, dof, out, base, alpha, leaf_out);
+      unpack_kernel<EPI_AXPY><<<grid, 256, 0, ctx->stream>>>((const double *)x.ret_val, (const int32_t *)x.ret_leaf,
+                                                           send_idx, x.n_send, dof, out, base, alpha, leaf_out);
     TB_CUDA(ctx, cudaGetLastError());
   }
   return TBSLAS_OK;

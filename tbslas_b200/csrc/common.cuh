@@ -113,6 +113,7 @@ struct tbslas_tree {
   double4 *d_geom = nullptr;   // [n_leaf+1] {cx, cy, cz, 2*2^depth}; [n_leaf] = null leaf
   uint8_t *d_depth = nullptr;  // [n_leaf]
   double *d_coeff = nullptr;   // [(n_leaf+1)*stride]; block n_leaf is all zero (null leaf)
+  bool replicated = false;  // multi-rank context, but every rank holds the WHOLE tree: no exchange
   // Morton-range sharding (nranks > 1)
   long long leaf_offset = 0;                 // global index of local leaf 0
   std::vector<uint64_t> splitters;           // first leaf key of every rank

@@ -115,6 +115,13 @@ def main():
     t1 = ctx.tree(one if rank == 0 else one.shard(0, 0))
     s1 = solo.tree(one)
     same("single-leaf tree", api.NodeFieldFunctor(t1)(pts.copy(), bc=0), api.NodeFieldFunctor(s1)(pts.copy(), bc=0))
+    # (4b) a velocity tree replicated on every rank: local evaluations, the step still exchanges
+    # points for the (sharded) advected tree
+    rvel = api.NodeFieldFunctor(ctx.tree(vels[1], replicated=True))
+    same("replicated velocity: eval", rvel(pts.copy(), bc=1), api.NodeFieldFunctor(svel[1])(pts.copy(), bc=1))
+    same("replicated velocity: semilag",
+         api.SolveSemilagRK2(rvel, api.NodeFieldFunctor(tcon), arr, 3, 0.05, 2, 1),
+         api.SolveSemilagRK2(api.NodeFieldFunctor(svel[1]), api.NodeFieldFunctor(scon), arr, 3, 0.05, 2, 1))
     # (5) empty point set on one rank (the call is still collective)
     e = pts[:0].copy() if rank == world - 1 else pts[:777].copy()
     same("ragged: empty input on the last rank", api.NodeFieldFunctor(tcon)(e.copy(), bc=0),
