@@ -121,6 +121,9 @@ int tbslas_b200_tree_create_replicated(tbslas_ctx *ctx, int q, int dof, size_t n
 /* New coefficients on the same leaves (what SetTreeGridValues writes every step,
  * tree_utils.h:547-550). */
 int tbslas_b200_tree_update_coeff(tbslas_tree *tree, const double *coeff, int mem);
+/* Read the coefficients back, [n_leaf][dof][Ncoef] (e.g. after semilag_insitu_update, before
+ * the host refines the tree). */
+int tbslas_b200_tree_get_coeff(tbslas_tree *tree, double *coeff, int mem);
 int tbslas_b200_tree_destroy(tbslas_tree *tree);
 int tbslas_b200_tree_info(const tbslas_tree *tree, int *q, int *dof, size_t *n_leaf);
 
@@ -165,6 +168,25 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2,
 int tbslas_b200_semilag_insitu(const tbslas_field *f1, const tbslas_field *f2,
                                tbslas_tree *con, int bc, int timestep, double dt, int nrk,
                                double *out_vals, int mem);
+
+/* ---- values -> coefficients: tbslas::SetTreeGridValues (tree_utils.h:500-552) ------ */
+/* The point-to-coefficient matrix of degree q, M[(q+1)^3][Ncoef] row-major (host memory):
+ * what tbslas::GetPt2CoeffMatrix builds (cheb.h:166-196: pseudo-inverse of the basis matrix
+ * at the new_nodes grid).  Supplied by the caller once per degree so that host and device
+ * refits use the very same matrix; kept on the device by the context. */
+int tbslas_b200_set_pt2coeff(tbslas_ctx *ctx, int q, const double *M);
+/* coeff[leaf][dof][:] = vals[leaf][dof][:] * M  for every local leaf, written into the tree
+ * (one FP64 tensor-core GEMM).  point_major = 0: vals is [leaf][dof][P], the layout
+ * SetTreeGridValues consumes; 1: vals is [leaf*P][dof], the layout SolveSemilagRK2 produces
+ * (tree_ns.h:502-513 transposes between the two). */
+int tbslas_b200_tree_set_grid_values(tbslas_tree *tree, const double *vals, int point_major,
+                                     int mem);
+/* The whole tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) on the device: arrival points
+ * generated in HBM, advected, and `con`'s coefficients refitted in place -- nothing crosses
+ * PCIe.  Needs set_pt2coeff for con's degree. */
+int tbslas_b200_semilag_insitu_update(const tbslas_field *f1, const tbslas_field *f2,
+                                      tbslas_tree *con, int bc, int timestep, double dt,
+                                      int nrk);
 
 /* ---- uniform-grid cubic variant (tbslas::fast_interp, tree_functor.h:89-153) - */
 /* grid [dof][n_reg][n_reg][n_reg] (x fastest), node centred on [0,1]^3. */

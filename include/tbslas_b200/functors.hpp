@@ -321,21 +321,39 @@ void SolveSemilagRK2(VFunctor &vel_evaluator, EFunctor &extrap_evaluator,
 }
 
 #ifdef SRC_TREE_UTILS_TREE_H_  // the reference's tree/tree_utils.h is in this translation unit
-// tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) with steps (1) and (2) on the GPU:
-// the arrival points are generated in HBM from the uploaded leaf list
-// (CollectChebTreeGridPoints, tree_utils.h:442-498) and never exist on the host; step (3)
-// is the reference's own SetTreeGridValues (tree_utils.h:500-552).
+// tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) entirely on the GPU: the arrival points
+// are generated in HBM from the uploaded leaf list (CollectChebTreeGridPoints,
+// tree_utils.h:442-498), advected, and refitted with the reference's own point-to-coefficient
+// matrix (GetPt2CoeffMatrix, cheb.h:166-196, uploaded once per degree) by one tensor-core
+// GEMM (SetTreeGridValues, tree_utils.h:500-552); only the new coefficients come back.
 template <class TreeType, class TreeFunc>
 void SolveSemilagInSitu(TreeFunc &tvel_func, TreeType &tree_curr, const int timestep,
                         const typename TreeType::Real_t dt, int num_rk_step = 1, bool /*adaptive*/ = true) {
   typedef typename TreeType::Real_t RealType;
+  typedef typename TreeType::Node_t NodeType;
   NodeFieldFunctor<RealType, TreeType> con(&tree_curr);
-  DeviceTree<TreeType> &dt_con = con.device_tree();
-  const size_t d = dt_con.cheb_deg() + 1, n = dt_con.n_leaf() * d * d * d;
-  std::vector<RealType> vals(n * dt_con.dof());
-  tvel_func.ctx.check(tbslas_b200_semilag_insitu(&tvel_func.field, nullptr, dt_con.get(), CurrentBC(), timestep, dt,
-                                                 num_rk_step, vals.data(), TBSLAS_MEM_HOST));
-  tbslas::SetTreeGridValues(tree_curr, dt_con.cheb_deg(), dt_con.dof(), vals);
+  DeviceTree<TreeType> &dcon = con.device_tree();
+  const Context &ctx = dcon.context();
+  const int q = dcon.cheb_deg(), dof = dcon.dof();
+  static int uploaded_q = -1;
+  if (uploaded_q != q) {
+    pvfmm::Matrix<RealType> M;
+    tbslas::GetPt2CoeffMatrix<RealType>(q, M);
+    ctx.check(tbslas_b200_set_pt2coeff(ctx.get(), q, &M[0][0]));
+    uploaded_q = q;
+  }
+  ctx.check(tbslas_b200_semilag_insitu_update(&tvel_func.field, nullptr, dcon.get(), CurrentBC(), timestep, dt,
+                                              num_rk_step));
+  const size_t nc = (size_t)(q + 1) * (q + 2) * (q + 3) / 6 * dof;
+  std::vector<RealType> coeff(nc * dcon.n_leaf());
+  ctx.check(tbslas_b200_tree_get_coeff(dcon.get(), coeff.data(), TBSLAS_MEM_HOST));
+  std::vector<NodeType *> &all = tree_curr.GetNodeList();
+  size_t j = 0;
+  for (size_t i = 0; i < all.size(); i++)
+    if (all[i]->IsLeaf() && !all[i]->IsGhost()) {
+      std::memcpy(&(all[i]->ChebData()[0]), &coeff[j * nc], nc * sizeof(RealType));
+      j++;
+    }
 }
 #endif
 

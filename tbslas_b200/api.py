@@ -124,6 +124,16 @@ class Context:
         evaluations on it never exchange points (tbslas_b200_tree_create_replicated)."""
         return Tree(self, ft.q, ft.dof, ft.coord, ft.depth, ft.coeff, replicated)
 
+    def set_pt2coeff(self, q: int, M=None) -> None:
+        """Upload the point-to-coefficient matrix of degree q (cheb.h:166-196); by default the
+        harness' numpy pseudo-inverse (flat_tree.pt2coeff)."""
+        if M is None:
+            from . import flat_tree as ftm
+            M = ftm.pt2coeff(q)
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        assert M.shape == ((q + 1) ** 3, (q + 1) * (q + 2) * (q + 3) // 6)
+        self.check(self.lib.tbslas_b200_set_pt2coeff(self.h, int(q), M.ctypes.data))
+
     # -- cubic grid (tbslas::fast_interp) ----------------------------------
     def fast_interp(self, grid, dof: int, n_reg: int, pts, out=None):
         n = pts.shape[0]
@@ -186,6 +196,19 @@ class Tree:
         if self.h:
             self.ctx.lib.tbslas_b200_tree_destroy(self.h)
             self.h = None
+
+    def set_grid_values(self, vals, point_major: bool = False) -> None:
+        """tbslas::SetTreeGridValues (tree_utils.h:500-552): refit the coefficients from grid
+        values ([leaf][dof][P], or [leaf*P][dof] when point_major)."""
+        a, m = _addr(vals)
+        self.ctx.check(self.ctx.lib.tbslas_b200_tree_set_grid_values(self.h, a, int(point_major), m))
+
+    def coefficients(self) -> np.ndarray:
+        """Read the device coefficients back: [n_leaf, dof, Ncoef] (tests)."""
+        nc = (self.q + 1) * (self.q + 2) * (self.q + 3) // 6
+        out = np.empty((self.n_leaf, self.dof, nc))
+        self.ctx.check(self.ctx.lib.tbslas_b200_tree_get_coeff(self.h, out.ctypes.data, MEM_HOST))
+        return out
 
     def collect_grid_points(self, device: bool = False):
         """tbslas::CollectChebTreeGridPoints: [n_leaf*(q+1)^3, 3]."""
@@ -331,6 +354,17 @@ def SolveSemilagInSitu(tvel_func: _Functor, tree_curr: Tree, timestep: int, dt: 
         C.byref(tvel_func.field), C.byref(tvel_extrap.field) if tvel_extrap is not None else None,
         tree_curr.h, bc, int(timestep), float(dt), int(num_rk_step), a, m))
     return out
+
+
+def SolveSemilagInSituUpdate(tvel_func: _Functor, tree_curr: Tree, timestep: int, dt: float,
+                             num_rk_step: int = 1, bc: int = FREESPACE,
+                             tvel_extrap: Optional[_Functor] = None) -> None:
+    """The whole tbslas::SolveSemilagInSitu on the device: tree_curr's coefficients are
+    replaced by the advected field's (needs Context.set_pt2coeff(q))."""
+    ctx = tree_curr.ctx
+    ctx.check(ctx.lib.tbslas_b200_semilag_insitu_update(
+        C.byref(tvel_func.field), C.byref(tvel_extrap.field) if tvel_extrap is not None else None,
+        tree_curr.h, bc, int(timestep), float(dt), int(num_rk_step)))
 
 
 def new_nodes(q: int) -> np.ndarray:

@@ -24,10 +24,11 @@ SYMBOLS = [
     "tbslas_b200_synchronize", "tbslas_b200_last_error", "tbslas_b200_version",
     "tbslas_b200_comm_unique_id", "tbslas_b200_comm_init", "tbslas_b200_comm_rank",
     "tbslas_b200_comm_last_exchange",
-    "tbslas_b200_tree_create", "tbslas_b200_tree_create_replicated", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_destroy",
+    "tbslas_b200_tree_create", "tbslas_b200_tree_create_replicated", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_get_coeff", "tbslas_b200_tree_destroy",
     "tbslas_b200_tree_info", "tbslas_b200_eval", "tbslas_b200_eval_set4",
     "tbslas_b200_eval_extrap", "tbslas_b200_eval_field", "tbslas_b200_traj_rk2",
-    "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_cubic_eval", "tbslas_b200_collect_grid_points",
+    "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_set_pt2coeff",
+    "tbslas_b200_tree_set_grid_values", "tbslas_b200_semilag_insitu_update", "tbslas_b200_cubic_eval", "tbslas_b200_collect_grid_points",
     "tbslas_b200_new_nodes", "tbslas_b200_point_key", "tbslas_b200_owner_of_key",
     "tbslas_b200_partition_leaves", "tbslas_b200_profile_enable", "tbslas_b200_profile_reset",
     "tbslas_b200_profile_num_stages", "tbslas_b200_profile_stage_name",
@@ -74,6 +75,7 @@ def load() -> C.CDLL:
                                           C.POINTER(vp)]
     L.tbslas_b200_tree_create_replicated.argtypes = L.tbslas_b200_tree_create.argtypes
     L.tbslas_b200_tree_update_coeff.argtypes = [vp, dp, C.c_int]
+    L.tbslas_b200_tree_get_coeff.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_tree_destroy.argtypes = [vp]
     L.tbslas_b200_tree_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                         C.POINTER(sz)]
@@ -89,6 +91,10 @@ def load() -> C.CDLL:
                                           sz, C.c_int, C.c_double, C.c_int, dp, dp, C.c_int]
     L.tbslas_b200_semilag_insitu.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int,
                                              C.c_int, C.c_double, C.c_int, dp, C.c_int]
+    L.tbslas_b200_set_pt2coeff.argtypes = [vp, C.c_int, dp]
+    L.tbslas_b200_tree_set_grid_values.argtypes = [vp, dp, C.c_int, C.c_int]
+    L.tbslas_b200_semilag_insitu_update.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int,
+                                                    C.c_int, C.c_double, C.c_int]
     L.tbslas_b200_cubic_eval.argtypes = [vp, dp, C.c_int, C.c_int, dp, sz, dp, C.c_int]
     L.tbslas_b200_collect_grid_points.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_new_nodes.argtypes = [C.c_int, C.POINTER(C.c_double)]

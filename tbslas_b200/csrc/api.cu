@@ -83,7 +83,7 @@ static int prof_collect(tbslas_ctx *ctx) {
 
 static const char *kStageNames[ST_COUNT] = {"H2D",     "D2H",       "Locate", "Bin",
                                             "ChebEval", "Combine",   "CubicGrid", "Pack",
-                                            "Exchange", "Unpack",    "GridPoints"};
+                                            "Exchange", "Unpack",    "GridPoints", "Refit"};
 
 // multi-rank pieces (comm.cu)
 int comm_tree_splitters(tbslas_tree *t, uint64_t first_key);
@@ -453,6 +453,8 @@ int tbslas_b200_finalize(tbslas_ctx *ctx) {
   }
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  for (Pt2Coeff &m : ctx->pt2coeff)
+    if (m.d_M) cudaFree(m.d_M);
   for (auto &pair : ctx->ev_pipe)
     for (cudaEvent_t &e : pair)
       if (e) cudaEventDestroy(e);
@@ -580,6 +582,20 @@ int tbslas_b200_tree_update_coeff(tbslas_tree *t, const double *coeff, int mem) 
                                  t->n_leaf * t->dof,
                                  mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice
                                                           : cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_tree_get_coeff(tbslas_tree *t, double *coeff, int mem) {
+  if (!t || (t->n_leaf && !coeff)) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  if (!t->n_leaf) return TBSLAS_OK;
+  const size_t ncoef_pad = t->stride / t->dof;
+  StageScope sc(ctx, ST_D2H, (double)(t->n_leaf * t->dof * t->ncoef * 8), 0);
+  TB_CUDA(ctx, cudaMemcpy2DAsync(coeff, t->ncoef * sizeof(double), t->d_coeff, ncoef_pad * sizeof(double),
+                                 t->ncoef * sizeof(double), t->n_leaf * t->dof,
+                                 mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                                  ctx->stream));
   if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TBSLAS_OK;
@@ -766,6 +782,36 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2, tbsl
 int tbslas_b200_semilag_insitu(const tbslas_field *f1, const tbslas_field *f2, tbslas_tree *con, int bc,
                                int timestep, double dt, int nrk, double *out_vals, int mem) {
   return semilag_impl(f1, f2, con, bc, nullptr, 0, timestep, dt, nrk, out_vals, nullptr, mem);
+}
+
+// ---------------------------------------------------------------- values -> coefficients
+int tbslas_b200_set_pt2coeff(tbslas_ctx *ctx, int q, const double *M) {
+  if (!ctx || !M) return TBSLAS_ERR_INVALID;
+  if (q < 1 || q > TBSLAS_MAX_CHEB_DEG) return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "degree %d not supported", q);
+  return set_pt2coeff(ctx, q, M);
+}
+
+int tbslas_b200_tree_set_grid_values(tbslas_tree *t, const double *vals, int point_major, int mem) {
+  if (!t || (t->n_leaf && !vals)) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  const size_t d = t->q + 1, m = t->n_leaf * t->dof * d * d * d;
+  HostIO io{ctx, mem};
+  void *dv;
+  TB_TRY(io.h2d(WS_VAL_A, vals, sizeof(double) * m, &dv));
+  TB_TRY(launch_refit(ctx, t, (const double *)dv, point_major));
+  return io.finish();
+}
+
+int tbslas_b200_semilag_insitu_update(const tbslas_field *f1, const tbslas_field *f2, tbslas_tree *con,
+                                      int bc, int timestep, double dt, int nrk) {
+  if (!con) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = con->ctx;
+  const size_t d = con->q + 1, n = con->n_leaf * d * d * d;
+  void *dval;
+  TB_TRY(ws_get(ctx, WS_VAL_C, sizeof(double) * con->dof * (n + 1), &dval));
+  TB_TRY(semilag_impl(f1, f2, con, bc, nullptr, 0, timestep, dt, nrk, (double *)dval, nullptr, TBSLAS_MEM_DEVICE));
+  // new coefficients in place: every evaluation of `con` above is stream-ordered before this
+  return launch_refit(ctx, con, (const double *)dval, /*point_major=*/1);
 }
 
 // ---------------------------------------------------------------- cubic grid

@@ -28,6 +28,7 @@ enum Stage {
   ST_EXCHANGE,  // NCCL all-to-all-v                       (OutScatterForward/Reverse)
   ST_UNPACK,
   ST_GRIDPTS,   // arrival point generation                (CollectChebTreeGridPoints)
+  ST_REFIT,     // values -> coefficients GEMM              (SetTreeGridValues)
   ST_COUNT
 };
 
@@ -67,6 +68,11 @@ enum Slot {
   WS_COUNT_SLOTS
 };
 
+struct Pt2Coeff {  // point-to-coefficient matrix of one degree, zero-padded to [Kp][Np]
+  double *d_M = nullptr;
+  int Kp = 0, Np = 0;
+};
+
 struct ProfRec {
   int stage;
   cudaEvent_t a, b;
@@ -99,6 +105,7 @@ struct tbslas_ctx {
   // host-buffer calls: H2D / compute / D2H of consecutive chunks overlap on three streams
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_pipe[5][2] = {};  // [in, phaseA, pos_out, phaseB, out][buffer parity]
+  tb::Pt2Coeff pt2coeff[TBSLAS_MAX_CHEB_DEG + 1];
   // pinned host scratch for small device->host reads (exchange counts: [nranks][nranks])
   unsigned *h_counts = nullptr;
 };
@@ -217,6 +224,9 @@ int launch_cubic_grid(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, c
 // gridpts.cu
 int launch_grid_points(tbslas_ctx *ctx, const tbslas_tree *t, double *out);
 void new_nodes_host(int q, double *x);  // tbslas::new_nodes 1-D table (host libm)
+// refit.cu
+int set_pt2coeff(tbslas_ctx *ctx, int q, const double *M_host);
+int launch_refit(tbslas_ctx *ctx, tbslas_tree *t, const double *vals, int point_major);
 // peak.cu
 int run_fp64_peak(tbslas_ctx *ctx, int reps, double *tflops);
 

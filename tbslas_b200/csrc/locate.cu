@@ -88,6 +88,7 @@ locate_kernel(const uint64_t *__restrict__ keys, int n_leaf, int periodic, doubl
   const size_t chunk0 = (size_t)blockIdx.x * (kLocateThreads * kLocItems);
   int my_bin[kLocItems], my_slot[kLocItems];
   uint32_t my_rank[kLocItems];
+  int guess = -1;  // leaf the previous batch of this warp resolved to (warp-uniform)
 
   auto claim = [&](int bin, unsigned m, int leader, int &slot, uint32_t &base) {
     // one table (or, on overflow, global) update for the lanes in m, all in `bin`
@@ -154,30 +155,42 @@ locate_kernel(const uint64_t *__restrict__ keys, int n_leaf, int periodic, doubl
     }
 
     // Warp-cooperative phase: departure points are spatially coherent, so most lanes of
-    // a warp share the leaf of the first unresolved lane.
+    // a warp share the leaf of the first unresolved lane -- and usually that leaf is the one
+    // this warp resolved for its previous batch of points (256 points earlier in the same
+    // leaf-major stream), which is tried first with two cached loads instead of a search.
     unsigned pending = __ballot_sync(0xffffffffu, todo);
-    for (int c = 0; c < kCoopIters && pending; c++) {
+    for (int c = 0; c < kCoopIters + 1 && pending; c++) {
       const int leader = __ffs(pending) - 1;
       const uint64_t lk = __shfl_sync(0xffffffffu, key, leader);
-      const int j = warp_count_le(keys, n_leaf, lk, lane) - 1;  // warp-uniform
+      int j;
+      if (c == 0) {
+        if (guess < 0) continue;
+        j = guess;
+      } else {
+        j = warp_count_le(keys, n_leaf, lk, lane) - 1;  // warp-uniform
+        guess = j;
+      }
       const uint64_t klo = (j >= 0) ? __ldg(keys + j) : 0ull;
       const bool last = (j + 1 >= n_leaf);
       const uint64_t khi = last ? ~0ull : __ldg(keys + j + 1);
       const bool hit = ((pending >> lane) & 1u) && key >= klo && (last || key < khi);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
-      const int b = (j >= 0) ? j : n_leaf;
-      int sl = -1;
-      uint32_t base = 0;
-      claim(b, m, leader, sl, base);
-      sl = __shfl_sync(0xffffffffu, sl, leader);
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (hit) {
-        bin = b;
-        slot = sl;
-        rank = base + __popc(m & lt);
+      if (m) {  // warp-uniform
+        const int b = (j >= 0) ? j : n_leaf;
+        const int claimer = __ffs(m) - 1;
+        int sl = -1;
+        uint32_t base = 0;
+        claim(b, m, claimer, sl, base);
+        sl = __shfl_sync(0xffffffffu, sl, claimer);
+        base = __shfl_sync(0xffffffffu, base, claimer);
+        if (hit) {
+          bin = b;
+          slot = sl;
+          rank = base + __popc(m & lt);
+        }
+        pending &= ~m;
       }
-      pending &= ~m;
-      if (__popc(m) < 4) break;  // incoherent input: stop paying for warp-wide searches
+      if (c > 0 && __popc(m) < 4) break;  // incoherent input: stop paying for warp-wide searches
     }
     if ((pending >> lane) & 1u) {  // per-lane fallback, updates aggregated per leaf
       const int j = lane_count_le(keys, n_leaf, key) - 1;

@@ -242,6 +242,57 @@ def test_gpu_semilag_insitu_equals_explicit_points(ctx):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("q,dof,n_leaf", [(4, 1, 8), (8, 3, 300), (14, 1, 137), (14, 3, 64), (5, 2, 1)])
+def test_gpu_refit_values_to_coefficients(ctx, q, dof, n_leaf):
+    """tbslas_b200_tree_set_grid_values (SetTreeGridValues, tree_utils.h:500-552) against the
+    same GEMM in numpy: 1e-12 of the coefficient scale; both value layouts."""
+    coord, dd = ftm.uniform_leaves(3)
+    ft = ftm.random_tree(coord[:n_leaf], dd[:n_leaf], q, dof, seed=q)
+    t = ctx.tree(ft)
+    M = ftm.pt2coeff(q)
+    ctx.set_pt2coeff(q, M)
+    P = (q + 1) ** 3
+    rng = np.random.default_rng(q + dof)
+    vals = rng.standard_normal((n_leaf, dof, P))
+    want = np.einsum("ldp,pn->ldn", vals, M)
+    t.set_grid_values(vals)
+    got = t.coefficients()
+    assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+    t.set_grid_values(np.ascontiguousarray(vals.transpose(0, 2, 1)), point_major=True)
+    assert np.abs(t.coefficients() - want).max() < 1e-12 * np.abs(want).max()
+    # evaluating a (globally continuous) field of total degree <= q on the grid and refitting
+    # reproduces its coefficients
+    def poly(p):
+        x, y, z = p[:, 0], p[:, 1], p[:, 2]
+        return np.stack([1 + x - 2 * y * z + x * x * y, x * y * z - 0.5 * z ** 3, 0.25 + y ** 2 * z - x ** 4][:dof],
+                        axis=1)
+    t.destroy()
+    fc, fd = ftm.uniform_leaves(1)  # the whole domain, so every grid point has a leaf
+    fp = ftm.fit(fc, fd, q, dof, poly)
+    t = ctx.tree(fp)
+    v = _api().NodeFieldFunctor(t)(ftm.grid_points(fc, fd, q), bc=0)  # [L*P, dof] point-major
+    t.set_grid_values(v, point_major=True)
+    assert np.abs(t.coefficients() - fp.coeff).max() < 1e-11 * np.abs(fp.coeff).max()
+    t.destroy()
+
+
+def test_gpu_semilag_insitu_update(ctx):
+    """The whole tree-level step on the device == step values refitted in numpy."""
+    api = _api()
+    coord, dd = adaptive_leaves(4, 2)
+    q = 6
+    tv = ftm.fit(coord, dd, q, 3, ftm.vel_rotation)
+    tc = ftm.fit(coord, dd, q, 1, lambda p: ftm.gaussian(p, (0.5, 0.5, 0.5), 0.25))
+    tvel, tcon = ctx.tree(tv), ctx.tree(tc)
+    vel = api.NodeFieldFunctor(tvel)
+    ctx.set_pt2coeff(q)
+    vals = api.SolveSemilagInSitu(vel, tcon, 1, 0.05, 1, 0)      # [L*P, 1]
+    want = np.einsum("lp,pn->ln", vals.reshape(tc.n_leaf, -1), ftm.pt2coeff(q))[:, None, :]
+    api.SolveSemilagInSituUpdate(vel, tcon, 1, 0.05, 1, 0)
+    got = tcon.coefficients()
+    assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+
+
 def test_gpu_cpp_dropin_binary():
     """The reference's own C++ templates over the product's header-only adaptors
     (oracle/dropin_test.cpp, prebuilt into oracle/_ref/ where /root/reference exists)."""
