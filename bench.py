@@ -38,6 +38,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def measured_traffic(workload, scale):
+    """DRAM bytes per launch of the evaluation kernel from the committed ncu capture of this
+    very command (profiles/r01_dram_cheb_eval_c2.csv: dram__bytes_read.sum + dram__bytes_write.sum
+    of the three launches of one full-size C2 step), or None for other workloads."""
+    p = os.path.join(ROOT, "profiles", "r01_dram_cheb_eval_c2.csv")
+    if workload.lower() != "c2" or scale != 0 or not os.path.exists(p):
+        return None, None
+    import csv
+    per = {}
+    for row in csv.reader(open(p)):
+        if len(row) > 14 and row[12].startswith("dram__bytes"):
+            per[row[0]] = per.get(row[0], 0.0) + float(row[14])
+    if not per:
+        return None, None
+    return sum(per.values()) / len(per), "profiles/r01_dram_cheb_eval_c2.csv (ncu, %d launches of one step)" % len(per)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -244,7 +261,14 @@ def run_b200(args):
         first = workloads.partition_leaves(wl.con.n_leaf, world)
         splitters = wl.con.keys()[first[:-1]]
         con_local = wl.con.shard(int(first[rank]), int(first[rank + 1]))
-        vel_local = wl.vel if args.replicate_velocity else \
+        vel_bytes = sum(v.coeff.nbytes for v in wl.vel)
+        # a velocity tree that is small next to 180 GB of HBM is held whole by every rank
+        # (SURVEY 8(f) f3): its two evaluations per step then need no point exchange; only the
+        # advected tree -- the big one -- is sharded and exchanged.  --shard-velocity forces the
+        # reference's layout (every tree partitioned by the same Morton break points).
+        replicate = (args.replicate_velocity or vel_bytes <= (1 << 30)) and not args.shard_velocity
+        args.replicate_velocity = replicate
+        vel_local = wl.vel if replicate else \
             [workloads.shard_by_splitters(v, splitters, rank) for v in wl.vel]
     else:
         con_local, vel_local = wl.con, wl.vel
@@ -309,6 +333,33 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
+    # ---- the other half of the metric: semi-Lagrangian step time of the tree-level call ---
+    # tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) entirely on the device: arrival points
+    # generated in HBM, advected, and the advected tree's coefficients refitted (one FP64
+    # tensor-core GEMM); run on a scratch copy of the tree so the timed workload stays the same.
+    ctx.set_pt2coeff(wl.q)
+    scratch = ctx.tree(con_local)
+    for _ in range(2):
+        api.SolveSemilagInSituUpdate(vel_f, scratch, 1, wl.dt, 1, wl.bc)
+        scratch.update_coeff(con_local.coeff)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    n_step = max(1, min(args.steps, 3))
+    for _ in range(n_step):
+        s0.record()
+        api.SolveSemilagInSituUpdate(vel_f, scratch, 1, wl.dt, 1, wl.bc)
+        s1.record()
+        barrier()
+        tot += s0.elapsed_time(s1)
+        scratch.update_coeff(con_local.coeff)
+    step_ms = tot / n_step
+    if world > 1:
+        t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    scratch.destroy()
+
     # ---- end to end: pinned host buffers through the C ABI -----------------------------
     h_pos = torch.empty((n_local, 3), dtype=torch.float64, pin_memory=True)
     h_pos.copy_(pos)
@@ -350,6 +401,7 @@ def run_b200(args):
     ach_tf = flops / (ev["ms"] * 1e-3) * 1e-12 if ev["ms"] > 0 else 0.0
     ach_gbs = bytes_alg / (ev["ms"] * 1e-3) * 1e-9 if ev["ms"] > 0 else 0.0
     stage_ms = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0}
+    traffic, traffic_src = measured_traffic(args.workload, args.scale)
     roofline = {
         "bound": "fp64", "kernel": "cheb_eval_kernel<q=%d>" % wl.q, "achieved": ach_tf,
         "peak": peak_fp64, "unit": "TFLOP/s", "frac": ach_tf / peak_fp64 if peak_fp64 else None,
@@ -357,7 +409,8 @@ def run_b200(args):
                        "no FP64 entry; nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2)",
         "flops_model": "reference's own: N*(9d + 2*dof*Ncoef), tree_functor.h:389-394",
         "avg_launch_ms": ev["ms"] / max(1, ev["launches"]), "launches": ev["launches"],
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": bytes_alg / max(1, ev["launches"]),
         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "peak_source": hbm_src,
                 "note": "algorithmic bytes (24 xyz + 8*dof out + coefficients once per leaf); the "
@@ -390,6 +443,9 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(n_local * 24), "d2h_bytes_per_step": int(n_local * 8),
                 "steps": e2e_steps, "checksum": checksum},
         "roofline": roofline,
+        "semilag_step": {"ms": step_ms, "what": "SolveSemilagInSitu on the device: arrival-point generation "
+                         "+ RK2 trajectories + scalar evaluation + values->coefficients refit, "
+                         "coefficients stay in HBM (tree_semilag.h:92-135)"},
     }
     if per_rank is not None:
         line["per_rank_stage_ms"] = per_rank
@@ -510,11 +566,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--scale", type=int, default=0, help="shrink the workload (tests)")
-    ap.add_argument("--cpu-leaves", type=int, default=1024,
+    ap.add_argument("--cpu-leaves", type=int, default=8192,
                     help="leaves in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--replicate-velocity", action="store_true",
-                    help="multi-GPU: every rank holds the whole velocity tree (SURVEY 8(f) row f3)")
+                    help="multi-GPU: every rank holds the whole velocity tree (SURVEY 8(f) row f3); "
+                         "default when the velocity trees take <= 1 GiB")
+    ap.add_argument("--shard-velocity", action="store_true",
+                    help="multi-GPU: partition the velocity tree like the advected tree (reference layout)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -522,6 +522,8 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   }
   std::vector<uint64_t> hk(n_leaf);
   std::vector<double4> hg(n_leaf + 1);
+  std::vector<uint4> hb(n_leaf + 1);
+  bool boxes_ok = true;
   for (size_t j = 0; j < n_leaf; j++) {
     if (hd[j] > kMaxDepth) return fail(ctx, TBSLAS_ERR_INVALID, "leaf %zu: depth %d > 15", j, hd[j]);
     hk[j] = leaf_key(hc[3 * j], hc[3 * j + 1], hc[3 * j + 2]);
@@ -530,8 +532,17 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
       return fail(ctx, TBSLAS_ERR_INVALID, "leaves must be in strictly ascending Morton order (leaf %zu)", j);
     // (x - c) * 2.0 * s, s = 2^depth (tree_functor.h:285-293): 2*s is exact
     hg[j] = make_double4(hc[3 * j], hc[3 * j + 1], hc[3 * j + 2], 2.0 * (double)(1ull << hd[j]));
+    // integer box of the octant (locate fast path): usable when every leaf is aligned to its
+    // own depth and ends before the next leaf begins
+    const unsigned sh = (unsigned)(kMaxDepth - hd[j]);
+    hb[j] = make_uint4((unsigned)floor(hc[3 * j] * 32768.0), (unsigned)floor(hc[3 * j + 1] * 32768.0),
+                       (unsigned)floor(hc[3 * j + 2] * 32768.0), sh);
+    const unsigned low = (1u << sh) - 1u;
+    if ((hb[j].x | hb[j].y | hb[j].z) & low) boxes_ok = false;
+    if (j && hk[j] - hk[j - 1] < (1ull << (3 * hb[j - 1].w))) boxes_ok = false;
   }
   hg[n_leaf] = make_double4(0, 0, 0, 2.0);  // null leaf: zero coefficients
+  hb[n_leaf] = make_uint4(0, 0, 0, 0);
   tbslas_tree *t = new tbslas_tree();
   t->ctx = ctx;
   t->q = q;
@@ -554,6 +565,9 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   TB_TREE_CUDA(cudaMalloc(&t->d_key, sizeof(uint64_t) * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMalloc(&t->d_geom, sizeof(double4) * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMalloc(&t->d_depth, n_leaf + 1));
+  TB_TREE_CUDA(cudaMalloc(&t->d_box, sizeof(uint4) * (n_leaf + 1)));
+  TB_TREE_CUDA(cudaMemcpy(t->d_box, hb.data(), sizeof(uint4) * (n_leaf + 1), cudaMemcpyHostToDevice));
+  t->boxes_ok = boxes_ok;
   TB_TREE_CUDA(cudaMalloc(&t->d_coeff, sizeof(double) * t->stride * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMemcpy(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice));
   TB_TREE_CUDA(cudaMemcpy(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice));
@@ -607,6 +621,7 @@ int tbslas_b200_tree_destroy(tbslas_tree *t) {
   cudaFree(t->d_key);
   cudaFree(t->d_geom);
   cudaFree(t->d_depth);
+  cudaFree(t->d_box);
   cudaFree(t->d_coeff);
   cudaFree(t->d_splitters);
   delete t;

@@ -119,6 +119,9 @@ struct tbslas_tree {
   uint64_t *d_key = nullptr;   // [n_leaf]   interleaved anchor keys, ascending
   double4 *d_geom = nullptr;   // [n_leaf+1] {cx, cy, cz, 2*2^depth}; [n_leaf] = null leaf
   uint8_t *d_depth = nullptr;  // [n_leaf]
+  uint4 *d_box = nullptr;      // [n_leaf+1] {ax, ay, az, 15-depth}: integer anchor at depth 15
+  bool boxes_ok = false;       // leaves are aligned, non-overlapping octants: "point inside the
+                               // box of leaf j" implies "j is the last leaf with key <= key(point)"
   double *d_coeff = nullptr;   // [(n_leaf+1)*stride]; block n_leaf is all zero (null leaf)
   bool replicated = false;  // multi-rank context, but every rank holds the WHOLE tree: no exchange
   // Morton-range sharding (nranks > 1)

@@ -54,6 +54,23 @@ TB_HD uint64_t point_key(double x, double y, double z, int periodic) {
   return spread3((uint32_t)fx) | (spread3((uint32_t)fy) << 1) | (spread3((uint32_t)fz) << 2);
 }
 
+// The same key from the integer anchors (device fast path: 32-bit logic only).  bit b of
+// an anchor goes to bit 3b (+0 x, +1 y, +2 z); the low 10 bits of each axis fill the low
+// 30 key bits, the high 5 bits the next 15.
+TB_HD uint32_t spread10(uint32_t v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+TB_HD uint64_t anchor_key(uint32_t ix, uint32_t iy, uint32_t iz) {
+  const uint32_t lo = spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2);
+  const uint32_t hi = spread10(ix >> 10) | (spread10(iy >> 10) << 1) | (spread10(iz >> 10) << 2);
+  return ((uint64_t)hi << 30) | lo;
+}
+
 // Cheb_Node::GetMortonId() = MortonId(Coord(), Depth()): anchor of the lower corner.
 TB_HD uint64_t leaf_key(double cx, double cy, double cz) { return point_key(cx, cy, cz, 1); }
 

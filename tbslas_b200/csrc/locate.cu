@@ -11,6 +11,8 @@
 // leaf id (histogram by warp-aggregated atomics -> scan -> scatter) builds the
 // grouping.  The assignment rule is unchanged: point p belongs to the last leaf j with
 // key(leaf j) <= key(p); the last leaf takes every larger key.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "keys.cuh"
 
@@ -69,12 +71,18 @@ __device__ __forceinline__ int table_slot(int *s_bin, int bin) {
 
 // Bins: 0..n_leaf-1 leaves, n_leaf = "no leaf" (evaluates to 0), n_leaf+2+r = points owned
 // by rank r (multi-rank only; count[] holds the send counts right after the leaf bins).
-template <bool MULTI>
+//
+// Fast path (BOXES: the leaves are aligned, non-overlapping octants): a point is first tested
+// against the integer box of the leaf this warp resolved last -- three XORs, a shift and a
+// compare on the depth-15 anchors floor(c * 2^15); inside the box implies "last leaf with
+// key <= key(point)", so the Morton key is only interleaved, and the leaf list only searched,
+// for the lanes that miss.  Departure points arrive in leaf-major order, so nearly all hit.
+template <bool MULTI, bool BOXES>
 __global__ void __launch_bounds__(kLocateThreads)
-locate_kernel(const uint64_t *__restrict__ keys, int n_leaf, int periodic, double *__restrict__ pos,
-              size_t n, int32_t *__restrict__ leaf_out, uint32_t *__restrict__ rank_out,
-              uint32_t *__restrict__ count, const uint64_t *__restrict__ splitters, int nranks,
-              int myrank) {
+locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes, int n_leaf, int periodic,
+              double *__restrict__ pos, size_t n, int32_t *__restrict__ leaf_out,
+              uint32_t *__restrict__ rank_out, uint32_t *__restrict__ count,
+              const uint64_t *__restrict__ splitters, int nranks, int myrank) {
   __shared__ int s_bin[kLocTable];
   __shared__ unsigned s_cnt[kLocTable];
   __shared__ unsigned s_base[kLocTable];
@@ -89,6 +97,8 @@ locate_kernel(const uint64_t *__restrict__ keys, int n_leaf, int periodic, doubl
   int my_bin[kLocItems], my_slot[kLocItems];
   uint32_t my_rank[kLocItems];
   int guess = -1;  // leaf the previous batch of this warp resolved to (warp-uniform)
+  uint4 gbox = make_uint4(0, 0, 0, 0);  // its integer box
+  int gslot = -2;                       // its row of the CTA table (-2: not looked up yet)
 
   auto claim = [&](int bin, unsigned m, int leader, int &slot, uint32_t &base) {
     // one table (or, on overflow, global) update for the lanes in m, all in `bin`
@@ -99,13 +109,30 @@ locate_kernel(const uint64_t *__restrict__ keys, int n_leaf, int periodic, doubl
     }
   };
 
+  // coordinates are fetched one batch ahead so their latency overlaps the previous batch
+  double nx = 0, ny = 0, nz = 0;
+  if (chunk0 + threadIdx.x < n) {
+    const size_t i0 = chunk0 + threadIdx.x;
+    nx = pos[3 * i0];
+    ny = pos[3 * i0 + 1];
+    nz = pos[3 * i0 + 2];
+  }
 #pragma unroll 1
   for (int it = 0; it < kLocItems; it++) {
     const size_t i = chunk0 + (size_t)it * kLocateThreads + threadIdx.x;
     const bool valid = i < n;
-    uint64_t key = 0;
+    // depth-15 anchors (tree_functor.h:464-479); `in` is false when any anchor leaves the
+    // 15-bit range or is NaN -- such a point has the saturated key (keys.cuh)
+    unsigned ix = 0, iy = 0, iz = 0;
+    bool in = false;
+    double x = nx, y = ny, z = nz;
+    if (it + 1 < kLocItems && i + kLocateThreads < n) {
+      const size_t i1 = i + kLocateThreads;
+      nx = pos[3 * i1];
+      ny = pos[3 * i1 + 1];
+      nz = pos[3 * i1 + 2];
+    }
     if (valid) {
-      double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
       if (periodic) {
         const double x0 = x, y0 = y, z0 = z;
         x = wrap_periodic(x);
@@ -115,93 +142,131 @@ locate_kernel(const uint64_t *__restrict__ keys, int n_leaf, int periodic, doubl
         if (y != y0) pos[3 * i + 1] = y;
         if (z != z0) pos[3 * i + 2] = z;
       }
-      key = point_key(x, y, z, periodic);
+      const double xs = x * 32768.0, ys = y * 32768.0, zs = z * 32768.0;  // exact
+      int jx = __double2int_rd(xs), jy = __double2int_rd(ys), jz = __double2int_rd(zs);
+      if (!periodic) {  // a coordinate == 1.0 moves down by 2^-15
+        if (xs == 32768.0) jx = 32767;
+        if (ys == 32768.0) jy = 32767;
+        if (zs == 32768.0) jz = 32767;
+      }
+      const double chk = xs + ys + zs;  // NaN if any is (the conversions above turn NaN into 0)
+      ix = (unsigned)jx;
+      iy = (unsigned)jy;
+      iz = (unsigned)jz;
+      in = ((ix | iy | iz) < 32768u) && (chk == chk);
     }
     int bin = 0, slot = -1;
     uint32_t rank = 0;
     bool todo = valid;
 
-    if (MULTI) {
-      // owner = last rank whose first-leaf key is <= key (rank 0 below the first)
-      bool mine = true;
-      int owner = myrank;
-      if (valid) {
-        mine = (key >= __ldg(splitters + myrank)) || myrank == 0;
-        if (myrank + 1 < nranks) mine = mine && key < __ldg(splitters + myrank + 1);
-        if (!mine) {
-          owner = 0;
-          for (int r = 1; r < nranks; r++)
-            if (__ldg(splitters + r) <= key) owner = r;
+    if (BOXES && guess >= 0) {  // warp-uniform
+      const bool hit = todo && in && ((((ix ^ gbox.x) | (iy ^ gbox.y) | (iz ^ gbox.z)) >> gbox.w) == 0u);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        const int claimer = __ffs(m) - 1;
+        if (gslot == -2) {  // first hit on this guess: find its row of the CTA table once
+          int sl = -1;
+          if (lane == claimer) sl = table_slot(s_bin, guess);
+          gslot = __shfl_sync(0xffffffffu, sl, claimer);
         }
-      }
-      unsigned out = __ballot_sync(0xffffffffu, valid && !mine);
-      while (out) {  // one aggregated update per destination rank present in the warp
-        const int leader = __ffs(out) - 1;
-        const int o = __shfl_sync(0xffffffffu, owner, leader);
-        const unsigned m = __ballot_sync(0xffffffffu, ((out >> lane) & 1u) && owner == o);
-        int sl = -1;
         uint32_t base = 0;
-        claim(n_leaf + 2 + o, m, leader, sl, base);
-        sl = __shfl_sync(0xffffffffu, sl, leader);
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if ((m >> lane) & 1u) {
-          bin = n_leaf + 2 + o;
-          slot = sl;
+        if (lane == claimer)
+          base = (gslot >= 0) ? atomicAdd(s_cnt + gslot, (unsigned)__popc(m))
+                              : atomicAdd(count + guess, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, claimer);
+        if (hit) {
+          bin = guess;
+          slot = gslot;
           rank = base + __popc(m & lt);
           todo = false;
         }
-        out &= ~m;
       }
     }
 
-    // Warp-cooperative phase: departure points are spatially coherent, so most lanes of
-    // a warp share the leaf of the first unresolved lane -- and usually that leaf is the one
-    // this warp resolved for its previous batch of points (256 points earlier in the same
-    // leaf-major stream), which is tried first with two cached loads instead of a search.
-    unsigned pending = __ballot_sync(0xffffffffu, todo);
-    for (int c = 0; c < kCoopIters + 1 && pending; c++) {
-      const int leader = __ffs(pending) - 1;
-      const uint64_t lk = __shfl_sync(0xffffffffu, key, leader);
-      int j;
-      if (c == 0) {
-        if (guess < 0) continue;
-        j = guess;
-      } else {
-        j = warp_count_le(keys, n_leaf, lk, lane) - 1;  // warp-uniform
-        guess = j;
+    if (__any_sync(0xffffffffu, todo)) {  // slow path: keys, owners, searches
+      const uint64_t key = in ? anchor_key(ix, iy, iz) : ~0ull;
+      if (MULTI) {
+        // owner = last rank whose first-leaf key is <= key (rank 0 below the first)
+        bool mine = true;
+        int owner = myrank;
+        if (todo) {
+          mine = (key >= __ldg(splitters + myrank)) || myrank == 0;
+          if (myrank + 1 < nranks) mine = mine && key < __ldg(splitters + myrank + 1);
+          if (!mine) {
+            owner = 0;
+            for (int r = 1; r < nranks; r++)
+              if (__ldg(splitters + r) <= key) owner = r;
+          }
+        }
+        unsigned out = __ballot_sync(0xffffffffu, todo && !mine);
+        while (out) {  // one aggregated update per destination rank present in the warp
+          const int leader = __ffs(out) - 1;
+          const int o = __shfl_sync(0xffffffffu, owner, leader);
+          const unsigned m = __ballot_sync(0xffffffffu, ((out >> lane) & 1u) && owner == o);
+          int sl = -1;
+          uint32_t base = 0;
+          claim(n_leaf + 2 + o, m, leader, sl, base);
+          sl = __shfl_sync(0xffffffffu, sl, leader);
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if ((m >> lane) & 1u) {
+            bin = n_leaf + 2 + o;
+            slot = sl;
+            rank = base + __popc(m & lt);
+            todo = false;
+          }
+          out &= ~m;
+        }
       }
-      const uint64_t klo = (j >= 0) ? __ldg(keys + j) : 0ull;
-      const bool last = (j + 1 >= n_leaf);
-      const uint64_t khi = last ? ~0ull : __ldg(keys + j + 1);
-      const bool hit = ((pending >> lane) & 1u) && key >= klo && (last || key < khi);
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (m) {  // warp-uniform
-        const int b = (j >= 0) ? j : n_leaf;
-        const int claimer = __ffs(m) - 1;
+
+      // Warp-cooperative phase: the lanes of a warp mostly share the leaf of the first
+      // unresolved lane.  Without boxes the previous batch's leaf is tried first by key range.
+      unsigned pending = __ballot_sync(0xffffffffu, todo);
+      for (int c = BOXES ? 1 : 0; c < kCoopIters + 1 && pending; c++) {
+        const int leader = __ffs(pending) - 1;
+        const uint64_t lk = __shfl_sync(0xffffffffu, key, leader);
+        int j;
+        if (c == 0) {
+          if (guess < 0) continue;
+          j = guess;
+        } else {
+          j = warp_count_le(keys, n_leaf, lk, lane) - 1;  // warp-uniform
+          guess = j;
+          gslot = -2;
+          if (BOXES && j >= 0) gbox = __ldg(boxes + j);
+        }
+        const uint64_t klo = (j >= 0) ? __ldg(keys + j) : 0ull;
+        const bool last = (j + 1 >= n_leaf);
+        const uint64_t khi = last ? ~0ull : __ldg(keys + j + 1);
+        const bool hit = ((pending >> lane) & 1u) && key >= klo && (last || key < khi);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {  // warp-uniform
+          const int b = (j >= 0) ? j : n_leaf;
+          const int claimer = __ffs(m) - 1;
+          int sl = -1;
+          uint32_t base = 0;
+          claim(b, m, claimer, sl, base);
+          sl = __shfl_sync(0xffffffffu, sl, claimer);
+          base = __shfl_sync(0xffffffffu, base, claimer);
+          if (hit) {
+            bin = b;
+            slot = sl;
+            rank = base + __popc(m & lt);
+          }
+          pending &= ~m;
+        }
+        if (c > 0 && __popc(m) < 4) break;  // incoherent input: stop paying for warp-wide searches
+      }
+      if ((pending >> lane) & 1u) {  // per-lane fallback, updates aggregated per leaf
+        const int j = lane_count_le(keys, n_leaf, key) - 1;
+        bin = (j >= 0) ? j : n_leaf;
+        const unsigned peers = __match_any_sync(pending, bin);
+        const int leader = __ffs(peers) - 1;
         int sl = -1;
         uint32_t base = 0;
-        claim(b, m, claimer, sl, base);
-        sl = __shfl_sync(0xffffffffu, sl, claimer);
-        base = __shfl_sync(0xffffffffu, base, claimer);
-        if (hit) {
-          bin = b;
-          slot = sl;
-          rank = base + __popc(m & lt);
-        }
-        pending &= ~m;
+        claim(bin, peers, leader, sl, base);
+        slot = __shfl_sync(peers, sl, leader);
+        rank = __shfl_sync(peers, base, leader) + __popc(peers & lt);
       }
-      if (c > 0 && __popc(m) < 4) break;  // incoherent input: stop paying for warp-wide searches
-    }
-    if ((pending >> lane) & 1u) {  // per-lane fallback, updates aggregated per leaf
-      const int j = lane_count_le(keys, n_leaf, key) - 1;
-      bin = (j >= 0) ? j : n_leaf;
-      const unsigned peers = __match_any_sync(pending, bin);
-      const int leader = __ffs(peers) - 1;
-      int sl = -1;
-      uint32_t base = 0;
-      claim(bin, peers, leader, sl, base);
-      slot = __shfl_sync(peers, sl, leader);
-      rank = __shfl_sync(peers, base, leader) + __popc(peers & lt);
     }
     my_bin[it] = valid ? bin : -1;
     my_slot[it] = slot;
@@ -230,16 +295,20 @@ int launch_locate(tbslas_ctx *ctx, const LocateArgs &a) {
   if (a.n == 0) return TBSLAS_OK;
   const size_t per_cta = (size_t)kLocateThreads * kLocItems;
   const unsigned grid = (unsigned)((a.n + per_cta - 1) / per_cta);
+  static const bool no_boxes = getenv("TBSLAS_LOCATE_NO_BOXES") && atoi(getenv("TBSLAS_LOCATE_NO_BOXES"));
+  const bool boxes = t->boxes_ok && !no_boxes;
+  if (multi && a.send_count != a.count + t->n_leaf + 2)
+    return fail(ctx, TBSLAS_ERR_INVALID, "send counts must follow the leaf bins");
+#define TB_LOCATE(M, B)                                                                          \
+  locate_kernel<M, B><<<grid, kLocateThreads, 0, ctx->stream>>>(                                 \
+      t->d_key, t->d_box, (int)t->n_leaf, a.periodic, a.pos, a.n, a.leaf, a.rank, a.count,       \
+      multi ? t->d_splitters : nullptr, multi ? ctx->nranks : 1, multi ? ctx->rank : 0)
   if (multi) {
-    if (a.send_count != a.count + t->n_leaf + 2)
-      return fail(ctx, TBSLAS_ERR_INVALID, "send counts must follow the leaf bins");
-    locate_kernel<true><<<grid, kLocateThreads, 0, ctx->stream>>>(
-        t->d_key, (int)t->n_leaf, a.periodic, a.pos, a.n, a.leaf, a.rank, a.count, t->d_splitters,
-        ctx->nranks, ctx->rank);
+    if (boxes) TB_LOCATE(true, true); else TB_LOCATE(true, false);
   } else {
-    locate_kernel<false><<<grid, kLocateThreads, 0, ctx->stream>>>(
-        t->d_key, (int)t->n_leaf, a.periodic, a.pos, a.n, a.leaf, a.rank, a.count, nullptr, 1, 0);
+    if (boxes) TB_LOCATE(false, true); else TB_LOCATE(false, false);
   }
+#undef TB_LOCATE
   TB_CUDA(ctx, cudaGetLastError());
   return TBSLAS_OK;
 }
