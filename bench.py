@@ -191,7 +191,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -215,7 +215,7 @@ def run_reference_cubic(args):
             ts.append(time.perf_counter() - t0)
     sec = float(np.mean(ts))
     rate = sp.shape[0] / sec
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "departure-point evals/sec", "value": rate, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -227,7 +227,7 @@ def run_reference_cubic(args):
                          "sample": "fast_interp on %d strided query points; the reference's loop is serial "
                                    "(tree_functor.h:106)" % sp.shape[0]},
         "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
     return 0
 
 
@@ -459,7 +459,7 @@ def run_b200(args):
                       % (nl, pts.shape[0], sec)}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -554,11 +554,31 @@ def run_b200_cubic(args):
         line["cpu_baseline"] = {"value": sp.shape[0] / sec, "unit": "points/s", "cores": 1, "kind": kind,
                                 "sample": "fast_interp on %d strided query points (%.1f s); the reference's loop "
                                           "is serial (tree_functor.h:106)" % (sp.shape[0], sec)}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything that libraries print to stdout while the bench runs (NCCL's version banner,
+    torchrun notices) goes to stderr; the one JSON line is written to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -94,8 +94,9 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
   const size_t chunk0 = (size_t)blockIdx.x * (kLocateThreads * kLocItems);
-  int my_bin[kLocItems], my_slot[kLocItems];
-  uint32_t my_rank[kLocItems];
+  // per point: (row of the CTA table + 1) << 24 | rank inside that row, completed with the
+  // row's global base once the whole CTA has counted (row 0: the rank is final already)
+  __shared__ uint32_t s_rec[kLocItems][kLocateThreads];
   int guess = -1;  // leaf the previous batch of this warp resolved to (warp-uniform)
   uint4 gbox = make_uint4(0, 0, 0, 0);  // its integer box
   int gslot = -2;                       // its row of the CTA table (-2: not looked up yet)
@@ -268,9 +269,15 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
         rank = __shfl_sync(peers, base, leader) + __popc(peers & lt);
       }
     }
-    my_bin[it] = valid ? bin : -1;
-    my_slot[it] = slot;
-    my_rank[it] = rank;
+    if (valid) {
+      leaf_out[i] = (bin <= n_leaf) ? bin : -2 - (bin - n_leaf - 2);
+      if (slot >= 0) {  // rank inside a table row: < points per CTA (2^11)
+        s_rec[it][threadIdx.x] = ((uint32_t)(slot + 1) << 24) | rank;
+      } else {          // table overflow: counted straight into the global bin, rank is final
+        s_rec[it][threadIdx.x] = 0u;
+        rank_out[i] = rank;
+      }
+    }
   }
 
   __syncthreads();
@@ -279,11 +286,10 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
   __syncthreads();
 #pragma unroll
   for (int it = 0; it < kLocItems; it++) {
-    if (my_bin[it] < 0) continue;
     const size_t i = chunk0 + (size_t)it * kLocateThreads + threadIdx.x;
-    const int b = my_bin[it];
-    leaf_out[i] = (b <= n_leaf) ? b : -2 - (b - n_leaf - 2);
-    rank_out[i] = my_rank[it] + (my_slot[it] >= 0 ? s_base[my_slot[it]] : 0u);
+    if (i >= n) break;
+    const uint32_t r = s_rec[it][threadIdx.x];
+    if (r >> 24) rank_out[i] = (r & 0xffffffu) + s_base[(r >> 24) - 1];
   }
 }
 
