@@ -96,9 +96,18 @@ void comm_destroy(tbslas_ctx *ctx);
 // ---------------------------------------------------------------------------
 // one tree evaluation on device buffers (tbslas::EvalTree, tree_functor.h:397-690)
 // ---------------------------------------------------------------------------
+// `same_as`: a tree that was evaluated at these very points by the previous call (nothing in
+// between): when it has the same leaf list the grouping left in the workspace is reused and
+// only the evaluation kernel runs (the four snapshots of a FieldSetFunctor, the two trees of
+// a FieldExtrapFunctor -- the reference sorts and searches once per tree).
+static bool same_leaves(const tbslas_tree *a, const tbslas_tree *b) {
+  return a && b && a->ctx == b->ctx && a->n_leaf == b->n_leaf && a->struct_hash == b->struct_hash &&
+         eval_tile_points(a) == eval_tile_points(b) && eval_needs_tile_map(a) == eval_needs_tile_map(b);
+}
+
 static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int epilogue,
                              double *out, const double *base, double alpha, int32_t *leaf_out,
-                             bool allow_exchange) {
+                             bool allow_exchange, const tbslas_tree *same_as = nullptr) {
   tbslas_ctx *ctx = t->ctx;
   if (n >= (size_t)0xfffffff0u)
     return fail(ctx, TBSLAS_ERR_INVALID, "n = %zu exceeds the 32-bit point index range", n);
@@ -126,6 +135,12 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
     TB_TRY(ws_get(ctx, WS_SENDIDX, sizeof(uint32_t) * (n + 1), &send_idx));
   }
 
+  static const bool exchange_first = !(getenv("TBSLAS_EXCHANGE_FIRST") && atoi(getenv("TBSLAS_EXCHANGE_FIRST")) == 0);
+  const bool reuse = !multi && !leaf_out && same_leaves(t, same_as) &&
+                     !(same_as->ctx->nranks > 1 && !same_as->replicated);
+  if (reuse) {  // the persistent evaluation kernel's work counter is the one thing to reset
+    TB_CUDA(ctx, cudaMemsetAsync((uint32_t *)count + t->n_leaf + 2 + kMaxRanks, 0, sizeof(uint32_t), ctx->stream));
+  } else {
   LocateArgs la;
   la.tree = t;
   la.periodic = (bc == TBSLAS_PERIODIC);
@@ -161,11 +176,11 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   // The persistent evaluation kernel fills every SM, so an NCCL kernel enqueued behind it on
   // another stream could not start before it drains; posting the forward exchange FIRST lets the
   // outsiders travel while the insiders are evaluated (TBSLAS_EXCHANGE_FIRST=0: old order).
-  static const bool exchange_first = !(getenv("TBSLAS_EXCHANGE_FIRST") && atoi(getenv("TBSLAS_EXCHANGE_FIRST")) == 0);
   if (multi) {
     TB_CUDA(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
     if (exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
   }
+  }  // !reuse
 
   EvalArgs ea;
   ea.tree = t;
@@ -202,8 +217,9 @@ int eval_received_points(tbslas_tree *t, int bc, double *pos, size_t n, double *
 }
 
 static int eval_tree_dev(tbslas_tree *t, int bc, double *pos, size_t n, int epilogue, double *out,
-                         const double *base, double alpha, int32_t *leaf_out) {
-  return eval_local_points(t, bc, pos, n, epilogue, out, base, alpha, leaf_out, true);
+                         const double *base, double alpha, int32_t *leaf_out,
+                         const tbslas_tree *same_as = nullptr) {
+  return eval_local_points(t, bc, pos, n, epilogue, out, base, alpha, leaf_out, true, same_as);
 }
 
 static int check_field(tbslas_ctx **ctx_out, const tbslas_field *f, int *dof) {
@@ -239,14 +255,15 @@ static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos,
     TB_TRY(ws_get(ctx, WS_VAL_A, sizeof(double) * 4 * m, &va));
     double *v4 = (double *)va;
     for (int i = 0; i < 4; i++)
-      TB_TRY(eval_tree_dev(f->tree[i], bc, pos, n, EPI_STORE, v4 + i * m, nullptr, 0.0, nullptr));
+      TB_TRY(eval_tree_dev(f->tree[i], bc, pos, n, EPI_STORE, v4 + i * m, nullptr, 0.0, nullptr,
+                           i ? f->tree[i - 1] : nullptr));
     return launch_cubic_time(ctx, v4, m, f->times, tq, out, base, alpha, axpy);
   }
   // EXTRAP: tree[0] = previous, tree[1] = current; current first (tree_extrap_functor.h:59-66)
   TB_TRY(ws_get(ctx, WS_VAL_A, sizeof(double) * 2 * m, &va));
   double *vc = (double *)va, *vp = vc + m;
   TB_TRY(eval_tree_dev(f->tree[1], bc, pos, n, EPI_STORE, vc, nullptr, 0.0, nullptr));
-  TB_TRY(eval_tree_dev(f->tree[0], bc, pos, n, EPI_STORE, vp, nullptr, 0.0, nullptr));
+  TB_TRY(eval_tree_dev(f->tree[0], bc, pos, n, EPI_STORE, vp, nullptr, 0.0, nullptr, f->tree[1]));
   return launch_extrap(ctx, vc, vp, m, out, base, alpha, axpy);
 }
 
@@ -568,6 +585,14 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   TB_TREE_CUDA(cudaMalloc(&t->d_box, sizeof(uint4) * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMemcpy(t->d_box, hb.data(), sizeof(uint4) * (n_leaf + 1), cudaMemcpyHostToDevice));
   t->boxes_ok = boxes_ok;
+  {
+    uint64_t h = 1469598103934665603ull;  // FNV-1a over the leaf keys and depths
+    for (size_t j = 0; j < n_leaf; j++) {
+      h = (h ^ hk[j]) * 1099511628211ull;
+      h = (h ^ hd[j]) * 1099511628211ull;
+    }
+    t->struct_hash = h;
+  }
   TB_TREE_CUDA(cudaMalloc(&t->d_coeff, sizeof(double) * t->stride * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMemcpy(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice));
   TB_TREE_CUDA(cudaMemcpy(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice));

@@ -120,6 +120,8 @@ struct tbslas_tree {
   double4 *d_geom = nullptr;   // [n_leaf+1] {cx, cy, cz, 2*2^depth}; [n_leaf] = null leaf
   uint8_t *d_depth = nullptr;  // [n_leaf]
   uint4 *d_box = nullptr;      // [n_leaf+1] {ax, ay, az, 15-depth}: integer anchor at depth 15
+  uint64_t struct_hash = 0;    // hash of (keys, depths): trees with equal hashes and leaf counts
+                               // share their leaf list, so one locate/bin pass serves them all
   bool boxes_ok = false;       // leaves are aligned, non-overlapping octants: "point inside the
                                // box of leaf j" implies "j is the last leaf with key <= key(point)"
   double *d_coeff = nullptr;   // [(n_leaf+1)*stride]; block n_leaf is all zero (null leaf)
