@@ -213,6 +213,22 @@ int tbslas_b200_owner_of_key(uint64_t key, const uint64_t *splitters, int nranks
  * first[r] = r*n_leaf/nranks, first[nranks] = n_leaf. */
 int tbslas_b200_partition_leaves(size_t n_leaf, int nranks, size_t *first);
 
+/* ---- load balance and refinement hints --------------------------- */
+/* Contiguous Morton ranges of about equal total WEIGHT (e.g. last step's points per leaf):
+ * what tbslas::SemiMergeTree aims at with its point-count aware break points
+ * (tree_utils.h:672-675).  first[r] = first leaf of rank r, first[nranks] = n_leaf.  Host only. */
+int tbslas_b200_partition_leaves_weighted(size_t n_leaf, const double *weight, int nranks,
+                                          size_t *first);
+/* Points that the most recent evaluation of `tree` located in each of its LOCAL leaves -- this
+ * rank's own points plus those received from other ranks (the part_indx differences of
+ * tree_functor.h:190-198), [n_leaf]: the weights above.  TBSLAS_ERR_INVALID before the first
+ * evaluation. */
+int tbslas_b200_tree_last_point_counts(tbslas_tree *tree, uint32_t *counts, int mem);
+/* l2 norm of every local leaf's highest-degree coefficients (i+j+k == q, all dof), [n_leaf]:
+ * the input of a host-side refine/coarsen decision (the reference leaves that decision to
+ * PVFMM's RefineTree, tree_utils.h:117-118) without downloading the coefficients. */
+int tbslas_b200_tree_tail_norm(tbslas_tree *tree, double *tail, int mem);
+
 /* ---- instrumentation (pvfmm::Profile::Tic/Toc tags, tree_functor.h:463-674) -- */
 /* When enabled, every kernel stage is bracketed with CUDA events on the context's
  * stream.  `get` synchronises and returns accumulated milliseconds and launch counts

@@ -210,6 +210,18 @@ class Tree:
         self.ctx.check(self.ctx.lib.tbslas_b200_tree_get_coeff(self.h, out.ctypes.data, MEM_HOST))
         return out
 
+    def last_point_counts(self) -> np.ndarray:
+        """Points the most recent evaluation of this tree located in each local leaf."""
+        out = np.zeros(self.n_leaf, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.tbslas_b200_tree_last_point_counts(self.h, out.ctypes.data, MEM_HOST))
+        return out
+
+    def tail_norm(self) -> np.ndarray:
+        """l2 norm of every leaf's highest-degree coefficients (i+j+k == q, all dof)."""
+        out = np.zeros(self.n_leaf)
+        self.ctx.check(self.ctx.lib.tbslas_b200_tree_tail_norm(self.h, out.ctypes.data, MEM_HOST))
+        return out
+
     def collect_grid_points(self, device: bool = False):
         """tbslas::CollectChebTreeGridPoints: [n_leaf*(q+1)^3, 3]."""
         n = self.n_leaf * (self.q + 1) ** 3
@@ -365,6 +377,17 @@ def SolveSemilagInSituUpdate(tvel_func: _Functor, tree_curr: Tree, timestep: int
     ctx.check(ctx.lib.tbslas_b200_semilag_insitu_update(
         C.byref(tvel_func.field), C.byref(tvel_extrap.field) if tvel_extrap is not None else None,
         tree_curr.h, bc, int(timestep), float(dt), int(num_rk_step)))
+
+
+def partition_leaves_weighted(weight, nranks: int) -> np.ndarray:
+    """Contiguous Morton ranges of about equal total weight: first[r] .. first[r+1]."""
+    w = np.ascontiguousarray(weight, dtype=np.float64)
+    first = (C.c_size_t * (nranks + 1))()
+    rc = capi.load().tbslas_b200_partition_leaves_weighted(
+        w.shape[0], w.ctypes.data_as(C.POINTER(C.c_double)), int(nranks), first)
+    if rc != capi.OK:
+        raise TbslasError("partition_leaves_weighted failed: %d" % rc)
+    return np.array(list(first), dtype=np.int64)
 
 
 def new_nodes(q: int) -> np.ndarray:

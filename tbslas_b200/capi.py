@@ -30,7 +30,8 @@ SYMBOLS = [
     "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_set_pt2coeff",
     "tbslas_b200_tree_set_grid_values", "tbslas_b200_semilag_insitu_update", "tbslas_b200_cubic_eval", "tbslas_b200_collect_grid_points",
     "tbslas_b200_new_nodes", "tbslas_b200_point_key", "tbslas_b200_owner_of_key",
-    "tbslas_b200_partition_leaves", "tbslas_b200_profile_enable", "tbslas_b200_profile_reset",
+    "tbslas_b200_partition_leaves", "tbslas_b200_partition_leaves_weighted",
+    "tbslas_b200_tree_last_point_counts", "tbslas_b200_tree_tail_norm", "tbslas_b200_profile_enable", "tbslas_b200_profile_reset",
     "tbslas_b200_profile_num_stages", "tbslas_b200_profile_stage_name",
     "tbslas_b200_profile_get", "tbslas_b200_kernel_launches", "tbslas_b200_fp64_peak",
 ]
@@ -102,6 +103,9 @@ def load() -> C.CDLL:
     L.tbslas_b200_point_key.restype = C.c_uint64
     L.tbslas_b200_owner_of_key.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
     L.tbslas_b200_partition_leaves.argtypes = [sz, C.c_int, C.POINTER(sz)]
+    L.tbslas_b200_partition_leaves_weighted.argtypes = [sz, C.POINTER(C.c_double), C.c_int, C.POINTER(sz)]
+    L.tbslas_b200_tree_last_point_counts.argtypes = [vp, vp, C.c_int]
+    L.tbslas_b200_tree_tail_norm.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_profile_enable.argtypes = [vp, C.c_int]
     L.tbslas_b200_profile_reset.argtypes = [vp]
     L.tbslas_b200_profile_stage_name.argtypes = [C.c_int]

@@ -181,6 +181,12 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
     if (exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
   }
   }  // !reuse
+  // remember the points per leaf (insiders now; the pass over received points adds its own)
+  if (t->n_leaf) {
+    if (!t->d_pt_count) TB_CUDA(ctx, cudaMalloc(&t->d_pt_count, sizeof(uint32_t) * t->n_leaf));
+    TB_TRY(launch_keep_counts(ctx, (const uint32_t *)count, t->d_pt_count, t->n_leaf, !allow_exchange));
+    t->pt_count_valid = true;
+  }
 
   EvalArgs ea;
   ea.tree = t;
@@ -647,6 +653,7 @@ int tbslas_b200_tree_destroy(tbslas_tree *t) {
   cudaFree(t->d_geom);
   cudaFree(t->d_depth);
   cudaFree(t->d_box);
+  cudaFree(t->d_pt_count);
   cudaFree(t->d_coeff);
   cudaFree(t->d_splitters);
   delete t;
@@ -906,6 +913,52 @@ int tbslas_b200_partition_leaves(size_t n_leaf, int nranks, size_t *first) {
   if (nranks < 1 || !first) return TBSLAS_ERR_INVALID;
   for (int r = 0; r <= nranks; r++) first[r] = (size_t)r * n_leaf / nranks;
   return TBSLAS_OK;
+}
+
+int tbslas_b200_partition_leaves_weighted(size_t n_leaf, const double *weight, int nranks, size_t *first) {
+  if (nranks < 1 || !first || (n_leaf && !weight)) return TBSLAS_ERR_INVALID;
+  double total = 0.0;
+  for (size_t j = 0; j < n_leaf; j++) {
+    if (!(weight[j] >= 0.0)) return TBSLAS_ERR_INVALID;  // negative or NaN
+    total += weight[j];
+  }
+  if (!(total > 0.0)) return tbslas_b200_partition_leaves(n_leaf, nranks, first);
+  // rank r starts at the first leaf whose weight prefix reaches r/nranks of the total
+  size_t j = 0;
+  double run = 0.0;
+  first[0] = 0;
+  for (int r = 1; r < nranks; r++) {
+    const double target = total * (double)r / (double)nranks;
+    while (j < n_leaf && run + 0.5 * weight[j] < target) run += weight[j++];
+    first[r] = j;
+  }
+  first[nranks] = n_leaf;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_tree_last_point_counts(tbslas_tree *t, uint32_t *counts, int mem) {
+  if (!t || (t->n_leaf && !counts)) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  if (!t->n_leaf) return TBSLAS_OK;
+  if (!t->pt_count_valid)
+    return fail(ctx, TBSLAS_ERR_INVALID, "tree_last_point_counts: this tree has not been evaluated yet");
+  TB_CUDA(ctx, cudaMemcpyAsync(counts, t->d_pt_count, sizeof(uint32_t) * t->n_leaf,
+                               mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                               ctx->stream));
+  if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_tree_tail_norm(tbslas_tree *t, double *tail, int mem) {
+  if (!t || (t->n_leaf && !tail)) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  if (!t->n_leaf) return TBSLAS_OK;
+  HostIO io{ctx, mem};
+  void *d;
+  TB_TRY(io.out_buf(WS_VAL_A, tail, sizeof(double) * t->n_leaf, &d));
+  TB_TRY(launch_tail_norm(ctx, t, (double *)d));
+  TB_TRY(io.d2h(tail, d, sizeof(double) * t->n_leaf));
+  return io.finish();
 }
 
 // ---------------------------------------------------------------- instrumentation

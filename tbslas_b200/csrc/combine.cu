@@ -133,6 +133,21 @@ __global__ void leaf_fixup_kernel(int32_t *leaf, size_t n, int n_leaf, long long
   leaf[i] = (j >= n_leaf) ? -1 : (int32_t)(j + offset);
 }
 
+// per-leaf point counts of an evaluation, kept with the tree (tbslas_b200_tree_last_point_counts)
+__global__ void keep_counts_kernel(const uint32_t *__restrict__ count, uint32_t *__restrict__ keep, size_t n,
+                                   int add) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) keep[j] = (add ? keep[j] : 0u) + count[j];
+}
+
+int launch_keep_counts(tbslas_ctx *ctx, const uint32_t *count, uint32_t *keep, size_t n_leaf, bool add) {
+  if (!n_leaf) return TBSLAS_OK;
+  keep_counts_kernel<<<(unsigned)((n_leaf + 255) / 256), 256, 0, ctx->stream>>>(count, keep, n_leaf, add ? 1 : 0);
+  TB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return TBSLAS_OK;
+}
+
 int launch_leaf_fixup(tbslas_ctx *ctx, int32_t *leaf, size_t n, size_t n_leaf, long long offset) {
   StageScope sc(ctx, ST_COMBINE, (double)n, 1);
   if (!n) return TBSLAS_OK;

@@ -120,6 +120,9 @@ struct tbslas_tree {
   double4 *d_geom = nullptr;   // [n_leaf+1] {cx, cy, cz, 2*2^depth}; [n_leaf] = null leaf
   uint8_t *d_depth = nullptr;  // [n_leaf]
   uint4 *d_box = nullptr;      // [n_leaf+1] {ax, ay, az, 15-depth}: integer anchor at depth 15
+  uint32_t *d_pt_count = nullptr;  // [n_leaf] points located in every leaf by the last evaluation
+                                   // (insiders + points received from other ranks)
+  bool pt_count_valid = false;
   uint64_t struct_hash = 0;    // hash of (keys, depths): trees with equal hashes and leaf counts
                                // share their leaf list, so one locate/bin pass serves them all
   bool boxes_ok = false;       // leaves are aligned, non-overlapping octants: "point inside the
@@ -222,6 +225,7 @@ int launch_extrap(tbslas_ctx *ctx, const double *vc, const double *vp, size_t m,
                   const double *base, double alpha, int axpy);
 int launch_axpy(tbslas_ctx *ctx, const double *base, const double *v, double alpha, size_t m,
                 double *out);
+int launch_keep_counts(tbslas_ctx *ctx, const uint32_t *count, uint32_t *keep, size_t n_leaf, bool add);
 int launch_leaf_fixup(tbslas_ctx *ctx, int32_t *leaf, size_t n, size_t n_leaf, long long offset);
 // cubic_grid.cu
 int launch_cubic_grid(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, const double *pos,
@@ -232,6 +236,8 @@ void new_nodes_host(int q, double *x);  // tbslas::new_nodes 1-D table (host lib
 // refit.cu
 int set_pt2coeff(tbslas_ctx *ctx, int q, const double *M_host);
 int launch_refit(tbslas_ctx *ctx, tbslas_tree *t, const double *vals, int point_major);
+// tailnorm.cu
+int launch_tail_norm(tbslas_ctx *ctx, const tbslas_tree *t, double *out);
 // peak.cu
 int run_fp64_peak(tbslas_ctx *ctx, int reps, double *tflops);
 

@@ -69,6 +69,25 @@ def test_partition_and_owner():
     assert lib.tbslas_b200_owner_of_key(3, spl, 2) == 0
 
 
+def test_weighted_partition():
+    """Equal weights reproduce equal-count ranges; skewed weights balance the weight, keep the
+    ranges contiguous and monotone; bad weights are rejected."""
+    from tbslas_b200.api import partition_leaves_weighted
+    assert partition_leaves_weighted(np.ones(10), 4).tolist() in ([0, 2, 5, 7, 10], [0, 3, 5, 8, 10])
+    rng = np.random.default_rng(3)
+    w = rng.uniform(0, 1, size=5000) ** 4
+    w[1000:1100] *= 50
+    for nr in (2, 3, 8):
+        first = partition_leaves_weighted(w, nr)
+        assert first[0] == 0 and first[-1] == w.size and np.all(np.diff(first) >= 0)
+        loads = np.array([w[first[r]:first[r + 1]].sum() for r in range(nr)])
+        assert loads.max() <= w.sum() / nr + w.max()
+    assert partition_leaves_weighted(np.zeros(7), 3).tolist() == [0, 2, 4, 7]   # no weight: by count
+    assert partition_leaves_weighted(np.array([5.0]), 4).tolist()[-1] == 1
+    with pytest.raises(Exception):
+        partition_leaves_weighted(np.array([1.0, -1.0]), 2)
+
+
 def test_new_nodes_matches_oracle(port):
     from tbslas_b200.api import new_nodes
     for q in range(1, 17):

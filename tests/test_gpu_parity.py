@@ -187,6 +187,58 @@ def test_gpu_partial_tree_null_leaf(ctx, port):
 
 
 @pytest.mark.parametrize("bc", [0, 1])
+def test_gpu_locate_faces_corners_and_leaf_major_streams(ctx, port, bc):
+    """The box fast path of the locate kernel: points exactly on leaf faces, edges
+    and corners (they belong to the upper neighbour), one ulp either side of them, the domain
+    faces 0 and 1, and a long leaf-major stream (the order departure points arrive in) must get
+    the oracle's leaf, bit for bit."""
+    api = _api()
+    coord, dd = adaptive_leaves(6, 2)
+    ft = ftm.random_tree(coord, dd, 3, 1, seed=21)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    size = np.power(0.5, dd.astype(np.float64))
+    rng = np.random.default_rng(77)
+    corners = (coord[:, None, :] + size[:, None, None] *
+               np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)], dtype=np.float64)[None]).reshape(-1, 3)
+    mids = coord + 0.5 * size[:, None]
+    faces = np.concatenate([np.where(np.arange(3) == a, coord + s * size[:, None], mids)
+                            for a in range(3) for s in (0.0, 1.0)])
+    special = np.concatenate([corners, faces, np.nextafter(corners, 0.0), np.nextafter(corners, 2.0),
+                              np.nextafter(faces, 0.0), np.nextafter(faces, 2.0)])
+    stream = ftm.grid_points(coord, dd, 5) - 0.013 * rng.standard_normal((1, 3))  # shifted arrival points
+    for pts in (special, stream, np.concatenate([stream[::7], special, stream[::5]])):
+        vo, lo, po = port.eval_tree(h, 1, pts, bc)
+        pos = pts.copy()
+        v, leaf = f.eval_with_leaf(pos, bc)
+        assert np.array_equal(leaf, lo)
+        assert np.array_equal(pos, po)
+        assert rel_err(v, vo) < RTOL
+
+
+def test_gpu_locate_overlapping_leaves_fall_back_to_keys(ctx, port):
+    """A leaf list that is NOT a set of disjoint octants (a depth-2 octant listed next to the
+    depth-1 octant that contains it): 'inside the box' no longer implies 'last leaf with key <=
+    key(point)', so the library must drop the box fast path and keep the reference's key rule."""
+    api = _api()
+    coord, dd = ftm.uniform_leaves(1)
+    extra = np.array([[0.25, 0.0, 0.0]])            # second x-child of leaf 0, depth 2
+    coord2 = np.concatenate([coord[:1], extra, coord[1:]])
+    dd2 = np.concatenate([dd[:1], np.array([2], dtype=dd.dtype), dd[1:]])
+    ft = ftm.random_tree(coord2, dd2, 4, 2, seed=5)
+    assert np.all(np.diff(ft.keys().astype(np.int64)) > 0)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    rng = np.random.default_rng(8)
+    pts = np.concatenate([rng.uniform(0, 0.5, size=(20000, 3)), rng.uniform(0, 1, size=(20000, 3))])
+    vo, lo, _ = port.eval_tree(h, 2, pts, 0)
+    v, leaf = f.eval_with_leaf(pts.copy(), 0)
+    assert (lo == 1).any() and (lo == 0).any()
+    assert np.array_equal(leaf, lo)
+    assert rel_err(v, vo) < RTOL
+
+
+@pytest.mark.parametrize("bc", [0, 1])
 @pytest.mark.parametrize("nrk", [1, 3])
 def test_gpu_traj_and_semilag_vs_oracle(ctx, port, bc, nrk):
     api = _api()
@@ -291,6 +343,27 @@ def test_gpu_semilag_insitu_update(ctx):
     api.SolveSemilagInSituUpdate(vel, tcon, 1, 0.05, 1, 0)
     got = tcon.coefficients()
     assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+
+
+def test_gpu_leaf_point_counts_and_tail_norm(ctx):
+    """Row f4 helpers: per-leaf point counts of the last evaluation == histogram of the leaf ids
+    it returned; tail norm == numpy on the packed coefficients."""
+    coord, dd = adaptive_leaves(5, 2)
+    q, dof = 6, 3
+    ft = ftm.random_tree(coord, dd, q, dof, seed=31)
+    t = ctx.tree(ft)
+    f = _api().NodeFieldFunctor(t)
+    pts = np.random.default_rng(12).uniform(0, 1, size=(200001, 3)) ** 2
+    _, leaf = f.eval_with_leaf(pts, 0)
+    assert np.array_equal(t.last_point_counts(), np.bincount(leaf, minlength=ft.n_leaf).astype(np.uint32))
+    f(pts[:1000], bc=0)
+    assert t.last_point_counts().sum() == 1000
+    shell = np.array([i + j + k == q for i in range(q + 1) for j in range(q + 1 - i)
+                      for k in range(q + 1 - i - j)])
+    want = np.sqrt((ft.coeff[:, :, shell] ** 2).sum(axis=(1, 2)))
+    got = t.tail_norm()
+    assert np.abs(got - want).max() <= 1e-14 * want.max()
+    t.destroy()
 
 
 def test_gpu_cpp_dropin_binary():
