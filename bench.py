@@ -383,6 +383,33 @@ def run_b200(args):
         e2e_s = float(t.item())
     checksum = float(np_vals.sum())
 
+    # ---- end to end, tree-level call: what a reference driver does per step through the drop-in
+    # adaptor of tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) -- upload the advected tree's
+    # coefficients from (pinned) host memory, run the step, read the new grid values back.  No
+    # point ever crosses PCIe: the arrival points are generated in HBM.
+    nc = ftm.ncoef(wl.q)
+    h_coef = torch.empty((con_local.n_leaf, 1, nc), dtype=torch.float64, pin_memory=True)
+    h_coef.copy_(torch.from_numpy(np.ascontiguousarray(con_local.coeff)))
+    np_coef = h_coef.numpy()
+
+    def step_tree():
+        tcon.update_coeff(np_coef)
+        ctx.check(ctx.lib.tbslas_b200_semilag_insitu(
+            api.C.byref(vel_f.field), None, tcon.h, wl.bc, 1, float(wl.dt), 1, np_vals.ctypes.data, 0))
+
+    step_tree()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_tree()
+    barrier()
+    tree_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([tree_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tree_s = float(t.item())
+    checksum_tree = float(np_vals.sum())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -441,7 +468,16 @@ def run_b200(args):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": n_total / e2e_s, "unit": "points/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(n_local * 24), "d2h_bytes_per_step": int(n_local * 8),
-                "steps": e2e_steps, "checksum": checksum},
+                "steps": e2e_steps, "checksum": checksum,
+                "what": "tbslas_b200_semilag_rk2 (SolveSemilagRK2) on pinned HOST arrays: arrival points "
+                        "in, advected values out, chunks pipelined over three streams",
+                "tree_level_call": {
+                    "value": n_total / tree_s, "unit": "points/s", "ms_per_step": tree_s * 1e3,
+                    "h2d_bytes_per_step": int(con_local.n_leaf * nc * 8), "d2h_bytes_per_step": int(n_local * 8),
+                    "checksum": checksum_tree,
+                    "what": "tbslas_b200_tree_update_coeff + tbslas_b200_semilag_insitu (SolveSemilagInSitu "
+                            "steps 1-2): coefficients up from pinned host memory, arrival points generated "
+                            "in HBM, values down"}},
         "roofline": roofline,
         "semilag_step": {"ms": step_ms, "what": "SolveSemilagInSitu on the device: arrival-point generation "
                          "+ RK2 trajectories + scalar evaluation + values->coefficients refit, "

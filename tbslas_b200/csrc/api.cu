@@ -344,6 +344,7 @@ struct PipeSpec {
   int val_dof = 0;
   int32_t *h_leaf = nullptr;      // [n], optional
   bool need_tmp = false;
+  size_t unit = 1;                // chunks are whole multiples of `unit` points (a leaf's grid)
 };
 enum { EV_IN = 0, EV_A, EV_POSOUT, EV_B, EV_OUT };
 
@@ -362,7 +363,8 @@ static int pipe_chunks(tbslas_ctx *ctx, size_t n) {
 template <class FA, class FB>
 static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA phase_a, FB phase_b) {
   const int K = pipe_chunks(ctx, n);
-  const size_t chunk = (n + K - 1) / K;
+  const size_t unit = sp.unit ? sp.unit : 1;
+  const size_t chunk = ((n / unit + K - 1) / K) * unit + (n % unit ? unit : 0);
   PipeBufs bufs[2] = {};
   const Slot pos_slot[2] = {WS_POS_A, WS_POS_C}, val_slot[2] = {WS_VAL_B, WS_VAL_C},
              leaf_slot[2] = {WS_LEAFOUT, WS_LEAFOUT2};
@@ -390,13 +392,15 @@ static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA p
     // ---- copy in (buffer b is free once chunk c-2 has been computed and copied out)
     TB_CUDA(ctx, cudaStreamWaitEvent(s_in, ev(EV_B, b), 0));
     TB_CUDA(ctx, cudaStreamWaitEvent(s_in, ev(EV_OUT, b), 0));
-    if (m) TB_CUDA(ctx, cudaMemcpyAsync(B.pos, sp.h_pos + 3 * off, sizeof(double) * 3 * m,
-                                        cudaMemcpyHostToDevice, s_in));
+    if (m && sp.h_pos) {
+      TB_CUDA(ctx, cudaMemcpyAsync(B.pos, sp.h_pos + 3 * off, sizeof(double) * 3 * m,
+                                   cudaMemcpyHostToDevice, s_in));
+      ctx->acc_units[ST_H2D] += (double)(24 * m);
+    }
     TB_CUDA(ctx, cudaEventRecord(ev(EV_IN, b), s_in));
-    ctx->acc_units[ST_H2D] += (double)(24 * m);
     // ---- compute
     TB_CUDA(ctx, cudaStreamWaitEvent(s_run, ev(EV_IN, b), 0));
-    TB_TRY(phase_a(B, m));
+    TB_TRY(phase_a(B, m, off));
     if (sp.h_pos_a) {
       TB_CUDA(ctx, cudaEventRecord(ev(EV_A, b), s_run));
       TB_CUDA(ctx, cudaStreamWaitEvent(s_out, ev(EV_A, b), 0));
@@ -406,7 +410,7 @@ static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA p
       TB_CUDA(ctx, cudaStreamWaitEvent(s_run, ev(EV_POSOUT, b), 0));  // phase B may wrap B.pos
       ctx->acc_units[ST_D2H] += (double)(24 * m);
     }
-    TB_TRY(phase_b(B, m));
+    TB_TRY(phase_b(B, m, off));
     TB_CUDA(ctx, cudaEventRecord(ev(EV_B, b), s_run));
     // ---- copy out
     TB_CUDA(ctx, cudaStreamWaitEvent(s_out, ev(EV_B, b), 0));
@@ -682,8 +686,8 @@ int tbslas_b200_eval_field(const tbslas_field *f, double tq, int bc, double *pos
   sp.h_val = out;
   sp.val_dof = dof;
   return run_host_pipeline(
-      ctx, sp, n, [](PipeBufs &, size_t) { return (int)TBSLAS_OK; },
-      [&](PipeBufs &B, size_t m) { return eval_field_dev(f, tq, bc, B.pos, m, B.val, 0, nullptr, 0.0); });
+      ctx, sp, n, [](PipeBufs &, size_t, size_t) { return (int)TBSLAS_OK; },
+      [&](PipeBufs &B, size_t m, size_t) { return eval_field_dev(f, tq, bc, B.pos, m, B.val, 0, nullptr, 0.0); });
 }
 
 int tbslas_b200_eval(tbslas_tree *t, int bc, double *pos, size_t n, double *out, int32_t *leaf_idx,
@@ -699,8 +703,8 @@ int tbslas_b200_eval(tbslas_tree *t, int bc, double *pos, size_t n, double *out,
   sp.val_dof = t->dof;
   sp.h_leaf = leaf_idx;
   return run_host_pipeline(
-      ctx, sp, n, [](PipeBufs &, size_t) { return (int)TBSLAS_OK; },
-      [&](PipeBufs &B, size_t m) { return eval_tree_dev(t, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, B.leaf); });
+      ctx, sp, n, [](PipeBufs &, size_t, size_t) { return (int)TBSLAS_OK; },
+      [&](PipeBufs &B, size_t m, size_t) { return eval_tree_dev(t, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, B.leaf); });
 }
 
 int tbslas_b200_eval_set4(tbslas_tree *const trees[4], const double times[4], double tq, int bc,
@@ -743,8 +747,8 @@ int tbslas_b200_traj_rk2(const tbslas_field *f1, const tbslas_field *f2, int bc,
     sp.need_tmp = true;
     return run_host_pipeline(
         ctx, sp, n,
-        [&](PipeBufs &B, size_t m) { return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk); },
-        [](PipeBufs &, size_t) { return (int)TBSLAS_OK; });
+        [&](PipeBufs &B, size_t m, size_t) { return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk); },
+        [](PipeBufs &, size_t, size_t) { return (int)TBSLAS_OK; });
   }
   void *xtmp;
   TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * n, &xtmp));
@@ -786,8 +790,26 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
     sp.need_tmp = true;
     return run_host_pipeline(
         ctx, sp, n,
-        [&](PipeBufs &B, size_t m) { return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk); },
-        [&](PipeBufs &B, size_t m) { return eval_tree_dev(con, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, nullptr); });
+        [&](PipeBufs &B, size_t m, size_t) { return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk); },
+        [&](PipeBufs &B, size_t m, size_t) { return eval_tree_dev(con, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, nullptr); });
+  }
+  if (mem == TBSLAS_MEM_HOST && insitu && n) {
+    // arrival points generated per chunk of leaves in HBM; the values of chunk c-1 travel to the
+    // host while chunk c is computed
+    const size_t P = (size_t)(con->q + 1) * (con->q + 1) * (con->q + 1);
+    PipeSpec sp;
+    sp.h_pos_a = out_dep;
+    sp.h_val = out_vals;
+    sp.val_dof = con->dof;
+    sp.need_tmp = true;
+    sp.unit = P;
+    return run_host_pipeline(
+        ctx, sp, n,
+        [&](PipeBufs &B, size_t m, size_t off) {
+          TB_TRY(launch_grid_points(ctx, con, B.pos, off / P, m / P));
+          return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk);
+        },
+        [&](PipeBufs &B, size_t m, size_t) { return eval_tree_dev(con, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, nullptr); });
   }
   HostIO io{ctx, mem};
   void *xsol, *xtmp, *dval;

@@ -53,8 +53,8 @@ enum {
 
 constexpr int kWtThreads = 32;  // one warp per CTA: every address below is CTA-uniform
 
-// Work distribution: tiles are handed out in chunks of `chunk` consecutive tiles from a
-// global counter (zeroed by the locate launcher), so a warp the scheduler favours simply
+// Work distribution: tiles are handed out in chunks of at most `chunk` consecutive tiles from a
+// global tile counter (zeroed by the locate launcher), so a warp the scheduler favours simply
 // takes more chunks and all workers finish together.
 template <int Q, int PPT, int EPI>
 __global__ void __launch_bounds__(kWtThreads, 8)
@@ -87,13 +87,19 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
       int *r = s_ctl + CT_RING + 3 * (n % 3);
       bool have = true;
       if (t >= (unsigned)s_cend) {  // take the next chunk
-        t = atomicAdd(chunk_counter, 1u) * chunk;
+        // guided self-scheduling: a share of what is left, so the chunks shrink towards the
+        // end of the launch and the workers finish within a couple of tiles of each other
+        const unsigned done = *reinterpret_cast<volatile unsigned *>(chunk_counter);
+        const unsigned rem = n_tiles > done ? n_tiles - done : 0u;
+        unsigned sz = rem / (2u * gridDim.x);
+        sz = sz < 2u ? 2u : (sz > chunk ? chunk : sz);
+        t = atomicAdd(chunk_counter, sz);
         if (t >= n_tiles) {
           have = false;
           s_ctl[CT_NEXT] = (int)n_tiles;
           s_cend = (int)n_tiles;
         } else {
-          s_cend = (int)min(t + chunk, n_tiles);
+          s_cend = (int)min(t + sz, n_tiles);
           // leaf of tile t = last bin j with tile_start[j] <= t
           int lo = 0, hi = p.n_bins;
           while (hi - lo > 1) {
@@ -288,9 +294,9 @@ int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
   size_t grid = a.max_tiles;
   if (grid > (size_t)8 * ctx->n_sm) grid = (size_t)8 * ctx->n_sm;
   if (grid == 0) return TBSLAS_OK;
-  // chunks of consecutive tiles (leaf locality) small enough to balance the tail
-  size_t chunk = a.max_tiles / (grid * 16);
-  chunk = chunk < 1 ? 1 : (chunk > 16 ? 16 : chunk);
+  // largest chunk of consecutive tiles (leaf locality); the kernel shrinks them towards the end
+  size_t chunk = a.max_tiles / (grid * 8);
+  chunk = chunk < 2 ? 2 : (chunk > 16 ? 16 : chunk);
   if (a.epilogue == EPI_STORE) {
     const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_STORE>(t);
     auto k = cheb_eval_wt_kernel<Q, PPT, EPI_STORE>;

@@ -231,7 +231,8 @@ int launch_leaf_fixup(tbslas_ctx *ctx, int32_t *leaf, size_t n, size_t n_leaf, l
 int launch_cubic_grid(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, const double *pos,
                       size_t n, double *out);
 // gridpts.cu
-int launch_grid_points(tbslas_ctx *ctx, const tbslas_tree *t, double *out);
+int launch_grid_points(tbslas_ctx *ctx, const tbslas_tree *t, double *out, size_t leaf0 = 0,
+                       size_t n_leaf = (size_t)-1);
 void new_nodes_host(int q, double *x);  // tbslas::new_nodes 1-D table (host libm)
 // refit.cu
 int set_pt2coeff(tbslas_ctx *ctx, int q, const double *M_host);

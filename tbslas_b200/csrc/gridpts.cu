@@ -43,14 +43,18 @@ __global__ void grid_points_kernel(const double4 *__restrict__ geom, const uint8
   out[i] = __dadd_rn(c, __dmul_rn(len, nodes.x[ix]));
 }
 
-int launch_grid_points(tbslas_ctx *ctx, const tbslas_tree *t, double *out) {
+// leaves [leaf0, leaf0 + n_leaf) of the tree -> out[n_leaf * P][3]
+int launch_grid_points(tbslas_ctx *ctx, const tbslas_tree *t, double *out, size_t leaf0, size_t n_leaf) {
+  if (leaf0 > t->n_leaf) leaf0 = t->n_leaf;
+  if (n_leaf > t->n_leaf - leaf0) n_leaf = t->n_leaf - leaf0;
   const int d = t->q + 1;
-  const size_t total = t->n_leaf * (size_t)d * d * d * 3;
+  const size_t total = n_leaf * (size_t)d * d * d * 3;
+  if (!total) return TBSLAS_OK;
   StageScope sc(ctx, ST_GRIDPTS, (double)(total / 3), 1);
   Nodes1D nodes;
   new_nodes_host(t->q, nodes.x);
   grid_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-      t->d_geom, t->d_depth, t->n_leaf, d, nodes, out);
+      t->d_geom + leaf0, t->d_depth + leaf0, n_leaf, d, nodes, out);
   TB_CUDA(ctx, cudaGetLastError());
   return TBSLAS_OK;
 }
