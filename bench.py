@@ -466,18 +466,22 @@ def run_b200(args):
                    {"collective": "NCCL all-to-all-v (grouped send/recv), forward xyz + reverse values",
                     "rank0_last_eval_sent": exch[0], "rank0_last_eval_received": exch[1]}},
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": n_total / e2e_s, "unit": "points/s", "ms_per_step": e2e_s * 1e3,
-                "h2d_bytes_per_step": int(n_local * 24), "d2h_bytes_per_step": int(n_local * 8),
-                "steps": e2e_steps, "checksum": checksum,
-                "what": "tbslas_b200_semilag_rk2 (SolveSemilagRK2) on pinned HOST arrays: arrival points "
-                        "in, advected values out, chunks pipelined over three streams",
-                "tree_level_call": {
-                    "value": n_total / tree_s, "unit": "points/s", "ms_per_step": tree_s * 1e3,
-                    "h2d_bytes_per_step": int(con_local.n_leaf * nc * 8), "d2h_bytes_per_step": int(n_local * 8),
-                    "checksum": checksum_tree,
-                    "what": "tbslas_b200_tree_update_coeff + tbslas_b200_semilag_insitu (SolveSemilagInSitu "
-                            "steps 1-2): coefficients up from pinned host memory, arrival points generated "
-                            "in HBM, values down"}},
+        # headline end-to-end number: the tree-level call every reference driver makes
+        # (SolveSemilagInSitu, advection.cpp:296) through the C ABI with pinned HOST buffers
+        "e2e": {"value": n_total / tree_s, "unit": "points/s", "ms_per_step": tree_s * 1e3,
+                "h2d_bytes_per_step": int(con_local.n_leaf * nc * 8), "d2h_bytes_per_step": int(n_local * 8),
+                "steps": e2e_steps, "checksum": checksum_tree,
+                "what": "tbslas_b200_tree_update_coeff + tbslas_b200_semilag_insitu (SolveSemilagInSitu "
+                        "steps 1-2, tree_semilag.h:92-130): the advected tree's coefficients up from pinned "
+                        "host memory, arrival points generated in HBM, advected grid values down to pinned "
+                        "host memory; leaf chunks pipelined (D2H of chunk c-1 under the kernels of chunk c)",
+                "point_array_call": {
+                    "value": n_total / e2e_s, "unit": "points/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(n_local * 24), "d2h_bytes_per_step": int(n_local * 8),
+                    "checksum": checksum,
+                    "what": "tbslas_b200_semilag_rk2 (SolveSemilagRK2, semilag.inc:27-45) on pinned HOST "
+                            "arrays: arrival points in (24 B/point over PCIe), advected values out; "
+                            "chunks pipelined over three streams"}},
         "roofline": roofline,
         "semilag_step": {"ms": step_ms, "what": "SolveSemilagInSitu on the device: arrival-point generation "
                          "+ RK2 trajectories + scalar evaluation + values->coefficients refit, "
