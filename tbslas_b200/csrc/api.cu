@@ -141,46 +141,46 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   if (reuse) {  // the persistent evaluation kernel's work counter is the one thing to reset
     TB_CUDA(ctx, cudaMemsetAsync((uint32_t *)count + t->n_leaf + 2 + kMaxRanks, 0, sizeof(uint32_t), ctx->stream));
   } else {
-  LocateArgs la;
-  la.tree = t;
-  la.periodic = (bc == TBSLAS_PERIODIC);
-  la.pos = pos;
-  la.n = n;
-  la.leaf = (int32_t *)leaf;
-  la.rank = (uint32_t *)rank;
-  la.count = (uint32_t *)count;
-  la.send_count = (uint32_t *)send_count;
-  TB_TRY(launch_locate(ctx, la));
-  if (multi) TB_TRY(comm_begin_exchange(ctx, (const uint32_t *)send_count));
+    LocateArgs la;
+    la.tree = t;
+    la.periodic = (bc == TBSLAS_PERIODIC);
+    la.pos = pos;
+    la.n = n;
+    la.leaf = (int32_t *)leaf;
+    la.rank = (uint32_t *)rank;
+    la.count = (uint32_t *)count;
+    la.send_count = (uint32_t *)send_count;
+    TB_TRY(launch_locate(ctx, la));
+    if (multi) TB_TRY(comm_begin_exchange(ctx, (const uint32_t *)send_count));
 
-  BinArgs ba;
-  ba.n_leaf = t->n_leaf;
-  ba.n = n;
-  ba.tile_pts = tile_pts;
-  ba.leaf = (const int32_t *)leaf;
-  ba.rank = (const uint32_t *)rank;
-  ba.count = (const uint32_t *)count;
-  ba.bin_start = (uint32_t *)bin_start;
-  ba.tile_start = (uint32_t *)tile_start;
-  ba.tile_map = (int2 *)tile_map;
-  ba.perm = (uint32_t *)perm;
-  ba.max_tiles = max_tiles;
-  if (multi) {
-    ba.pos = pos;
-    ba.send_count = (const uint32_t *)send_count;
-    ba.nranks = ctx->nranks;
-    ba.send_pos = (double *)send_pos;
-    ba.send_idx = (uint32_t *)send_idx;
+    BinArgs ba;
+    ba.n_leaf = t->n_leaf;
+    ba.n = n;
+    ba.tile_pts = tile_pts;
+    ba.leaf = (const int32_t *)leaf;
+    ba.rank = (const uint32_t *)rank;
+    ba.count = (const uint32_t *)count;
+    ba.bin_start = (uint32_t *)bin_start;
+    ba.tile_start = (uint32_t *)tile_start;
+    ba.tile_map = (int2 *)tile_map;
+    ba.perm = (uint32_t *)perm;
+    ba.max_tiles = max_tiles;
+    if (multi) {
+      ba.pos = pos;
+      ba.send_count = (const uint32_t *)send_count;
+      ba.nranks = ctx->nranks;
+      ba.send_pos = (double *)send_pos;
+      ba.send_idx = (uint32_t *)send_idx;
+    }
+    TB_TRY(launch_bin(ctx, ba));
+    // The persistent evaluation kernel fills every SM, so an NCCL kernel enqueued behind it on
+    // another stream could not start before it drains; posting the forward exchange FIRST lets the
+    // outsiders travel while the insiders are evaluated (TBSLAS_EXCHANGE_FIRST=0: old order).
+    if (multi) {
+      TB_CUDA(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+      if (exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
+    }
   }
-  TB_TRY(launch_bin(ctx, ba));
-  // The persistent evaluation kernel fills every SM, so an NCCL kernel enqueued behind it on
-  // another stream could not start before it drains; posting the forward exchange FIRST lets the
-  // outsiders travel while the insiders are evaluated (TBSLAS_EXCHANGE_FIRST=0: old order).
-  if (multi) {
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
-    if (exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
-  }
-  }  // !reuse
   // remember the points per leaf (insiders now; the pass over received points adds its own)
   if (t->n_leaf) {
     if (!t->d_pt_count) TB_CUDA(ctx, cudaMalloc(&t->d_pt_count, sizeof(uint32_t) * t->n_leaf));
