@@ -273,16 +273,28 @@ static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos,
   return launch_extrap(ctx, vc, vp, m, out, base, alpha, axpy);
 }
 
-// tbslas::ComputeTrajRK2 on device state: xsol [n][3] in/out, xtmp [n][3] scratch.
+// tbslas::ComputeTrajRK2 on device state: xsol [n][3] receives the end points, xtmp [n][3] is
+// scratch.  x0 = starting points: either xsol itself (in place, as the reference works on its
+// copy, traj.inc:57-64) or a separate read-only array, which saves the 48 B/point copy
+// xinit -> xsol -- only when the boundary is not periodic, because the periodic wrap rewrites the
+// evaluated positions in place (tree_functor.h:442-449) and the start array may be the caller's.
 static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, double *xsol,
-                        double *xtmp, size_t n, double tinit, double tfinal, int nrk) {
+                        double *xtmp, size_t n, double tinit, double tfinal, int nrk,
+                        const double *x0 = nullptr) {
   const double tau = (tfinal - tinit) / nrk;  // traj.inc:55
   double tcur = tinit;
+  tbslas_ctx *ctx = f1->tree[0]->ctx;
+  if (x0 && x0 != xsol && bc == TBSLAS_PERIODIC) {
+    StageScope sc(ctx, ST_COMBINE, (double)(24 * n), 0);
+    TB_CUDA(ctx, cudaMemcpyAsync(xsol, x0, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    x0 = xsol;
+  }
   for (int s = 0; s < nrk; s++) {
+    double *x = (s == 0 && x0) ? const_cast<double *>(x0) : xsol;  // not written unless periodic
     // v1 = V(x, t);  xtmp = x + 0.5*tau*v1      traj.inc:33-36 (x wrapped in place if periodic)
-    TB_TRY(eval_field_dev(f1, tcur, bc, xsol, n, xtmp, 1, xsol, 0.5 * tau));
+    TB_TRY(eval_field_dev(f1, tcur, bc, x, n, xtmp, 1, x, 0.5 * tau));
     // v2 = V(xtmp, t + tau/2);  x = x + tau*v2  traj.inc:40-42
-    TB_TRY(eval_field_dev(f2 ? f2 : f1, tcur + 0.5 * tau, bc, xtmp, n, xsol, 1, xsol, tau));
+    TB_TRY(eval_field_dev(f2 ? f2 : f1, tcur + 0.5 * tau, bc, xtmp, n, xsol, 1, x, tau));
     tcur = tcur + tau;
   }
   return TBSLAS_OK;
@@ -752,11 +764,7 @@ int tbslas_b200_traj_rk2(const tbslas_field *f1, const tbslas_field *f2, int bc,
   }
   void *xtmp;
   TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * n, &xtmp));
-  {  // xsol = xinit (traj.inc:57-58)
-    StageScope sc(ctx, ST_COMBINE, (double)(24 * n), 0);
-    TB_CUDA(ctx, cudaMemcpyAsync(out_pos, pos, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, ctx->stream));
-  }
-  return traj_rk2_dev(f1, f2, bc, out_pos, (double *)xtmp, n, tinit, tfinal, nrk);
+  return traj_rk2_dev(f1, f2, bc, out_pos, (double *)xtmp, n, tinit, tfinal, nrk, pos);
 }
 
 // pos == nullptr: the arrival points are generated on the device from `con`'s own leaves
@@ -821,11 +829,9 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
   TB_TRY(io.out_buf(WS_VAL_B, out_vals, sizeof(double) * con->dof * n, &dval));
   if (insitu) {
     if (n) TB_TRY(launch_grid_points(ctx, con, (double *)xsol));
-  } else {
-    StageScope sc(ctx, ST_COMBINE, (double)(24 * n), 0);
-    TB_CUDA(ctx, cudaMemcpyAsync(xsol, pos, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  TB_TRY(traj_rk2_dev(f1, f2, bc, (double *)xsol, (double *)xtmp, n, tinit, tfinal, nrk));
+  TB_TRY(traj_rk2_dev(f1, f2, bc, (double *)xsol, (double *)xtmp, n, tinit, tfinal, nrk,
+                      insitu ? (const double *)xsol : pos));
   if (mem == TBSLAS_MEM_DEVICE && out_dep && bc == TBSLAS_PERIODIC) {
     // keep the caller's departure points un-wrapped: evaluate on a copy
     TB_CUDA(ctx, cudaMemcpyAsync(xtmp, xsol, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice,
