@@ -607,6 +607,22 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   TB_TREE_CUDA(cudaMalloc(&t->d_box, sizeof(uint4) * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMemcpy(t->d_box, hb.data(), sizeof(uint4) * (n_leaf + 1), cudaMemcpyHostToDevice));
   t->boxes_ok = boxes_ok;
+  {  // cell table: depth g with about two cells per leaf, 1 <= g <= 6 (1 MiB)
+    int g = 1;
+    while (g < 6 && ((size_t)1 << (3 * g)) < 2 * n_leaf) g++;
+    const size_t n_cell = (size_t)1 << (3 * g);
+    t->cell_shift = 3 * (kMaxDepth - g);
+    std::vector<uint32_t> cell(n_cell + 2);
+    size_t j = 0;
+    for (size_t c = 0; c < n_cell; c++) {
+      const uint64_t first = (uint64_t)c << t->cell_shift;
+      while (j < n_leaf && hk[j] <= first) j++;
+      cell[c] = (uint32_t)j;
+    }
+    cell[n_cell] = cell[n_cell + 1] = (uint32_t)n_leaf;
+    TB_TREE_CUDA(cudaMalloc(&t->d_cell, sizeof(uint32_t) * cell.size()));
+    TB_TREE_CUDA(cudaMemcpy(t->d_cell, cell.data(), sizeof(uint32_t) * cell.size(), cudaMemcpyHostToDevice));
+  }
   {
     uint64_t h = 1469598103934665603ull;  // FNV-1a over the leaf keys and depths
     for (size_t j = 0; j < n_leaf; j++) {
@@ -669,6 +685,7 @@ int tbslas_b200_tree_destroy(tbslas_tree *t) {
   cudaFree(t->d_geom);
   cudaFree(t->d_depth);
   cudaFree(t->d_box);
+  cudaFree(t->d_cell);
   cudaFree(t->d_pt_count);
   cudaFree(t->d_coeff);
   cudaFree(t->d_splitters);

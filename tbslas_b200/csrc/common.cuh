@@ -120,6 +120,9 @@ struct tbslas_tree {
   double4 *d_geom = nullptr;   // [n_leaf+1] {cx, cy, cz, 2*2^depth}; [n_leaf] = null leaf
   uint8_t *d_depth = nullptr;  // [n_leaf]
   uint4 *d_box = nullptr;      // [n_leaf+1] {ax, ay, az, 15-depth}: integer anchor at depth 15
+  uint32_t *d_cell = nullptr;  // [8^g + 2] cell table of the locate kernel: number of leaf keys <= the
+                               // first key of every depth-g cell (g = (45 - cell_shift) / 3)
+  int cell_shift = 45;
   uint32_t *d_pt_count = nullptr;  // [n_leaf] points located in every leaf by the last evaluation
                                    // (insiders + points received from other ranks)
   bool pt_count_valid = false;

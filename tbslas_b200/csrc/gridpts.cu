@@ -28,19 +28,26 @@ void new_nodes_host(int q, double *x) {  // cheb.h:51-58
   }
 }
 
-__global__ void grid_points_kernel(const double4 *__restrict__ geom, const uint8_t *__restrict__ depth,
-                                   size_t n_leaf, int d, Nodes1D nodes, double *__restrict__ out) {
-  const size_t P = (size_t)d * d * d;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per scalar
-  if (i >= n_leaf * P * 3) return;
-  const size_t leaf = i / (3 * P);
-  const unsigned r = (unsigned)(i - leaf * 3 * P);
-  const unsigned pt = r / 3, a = r - 3 * pt;
-  const unsigned ix = (a == 0) ? pt % d : (a == 1) ? (pt / d) % d : pt / (d * d);
-  const double4 g = geom[leaf];
-  const double c = (a == 0) ? g.x : (a == 1) ? g.y : g.z;
-  const double len = 1.0 / (double)(1u << depth[leaf]);  // pow(0.5, depth), exact
-  out[i] = __dadd_rn(c, __dmul_rn(len, nodes.x[ix]));
+// One CTA per leaf (grid-stride over leaves), one thread per output scalar of that leaf: all index
+// arithmetic is 32-bit and the stores of a warp are one contiguous 256-B run.
+__global__ void __launch_bounds__(256)
+grid_points_kernel(const double4 *__restrict__ geom, const uint8_t *__restrict__ depth,
+                   size_t n_leaf, int d, Nodes1D nodes, double *__restrict__ out) {
+  __shared__ double s_node[TBSLAS_MAX_CHEB_DEG + 1];
+  if (threadIdx.x <= TBSLAS_MAX_CHEB_DEG) s_node[threadIdx.x] = nodes.x[threadIdx.x];
+  __syncthreads();
+  const unsigned ud = (unsigned)d, dd = ud * ud, P3 = 3u * dd * ud;
+  for (size_t leaf = blockIdx.x; leaf < n_leaf; leaf += gridDim.x) {
+    const double4 g = geom[leaf];
+    const double len = 1.0 / (double)(1u << depth[leaf]);  // pow(0.5, depth), exact
+    double *o = out + leaf * P3;
+    for (unsigned r = threadIdx.x; r < P3; r += blockDim.x) {
+      const unsigned pt = r / 3u, a = r - 3u * pt;
+      const unsigned ix = (a == 0) ? pt % ud : (a == 1) ? (pt / ud) % ud : pt / dd;
+      const double c = (a == 0) ? g.x : (a == 1) ? g.y : g.z;
+      o[r] = __dadd_rn(c, __dmul_rn(len, s_node[ix]));
+    }
+  }
 }
 
 // leaves [leaf0, leaf0 + n_leaf) of the tree -> out[n_leaf * P][3]
@@ -53,8 +60,9 @@ int launch_grid_points(tbslas_ctx *ctx, const tbslas_tree *t, double *out, size_
   StageScope sc(ctx, ST_GRIDPTS, (double)(total / 3), 1);
   Nodes1D nodes;
   new_nodes_host(t->q, nodes.x);
-  grid_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-      t->d_geom + leaf0, t->d_depth + leaf0, n_leaf, d, nodes, out);
+  const size_t want = n_leaf < (size_t)ctx->n_sm * 64 ? n_leaf : (size_t)ctx->n_sm * 64;
+  grid_points_kernel<<<(unsigned)want, 256, 0, ctx->stream>>>(t->d_geom + leaf0, t->d_depth + leaf0, n_leaf, d,
+                                                             nodes, out);
   TB_CUDA(ctx, cudaGetLastError());
   return TBSLAS_OK;
 }

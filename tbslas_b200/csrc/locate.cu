@@ -19,38 +19,6 @@
 namespace tb {
 
 constexpr int kLocateThreads = 256;
-constexpr int kCoopIters = 4;  // cooperative searches per warp before per-lane fallback
-
-// Cooperative 32-ary search by one warp: number of keys <= k (k warp-uniform).
-// Each level, lane t probes keys[lo + t*step]; the ballot of "probe <= k" is a
-// prefix of ones because the keys ascend, so its popcount selects the sub-range.
-__device__ __forceinline__ int warp_count_le(const uint64_t *__restrict__ keys, int n, uint64_t k,
-                                             int lane) {
-  int lo = 0, hi = n;  // answer in [lo, hi]
-  while (hi > lo) {
-    const int step = (hi - lo + 31) >> 5;
-    const int idx = lo + lane * step;
-    const bool le = (idx < hi) && (__ldg(keys + idx) <= k);
-    const int c = __popc(__ballot_sync(0xffffffffu, le));
-    if (c == 0) return lo;
-    const int nlo = lo + (c - 1) * step + 1;
-    hi = min(hi, lo + c * step);
-    lo = nlo;
-  }
-  return lo;
-}
-
-__device__ __forceinline__ int lane_count_le(const uint64_t *__restrict__ keys, int n, uint64_t k) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(keys + mid) <= k)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  return lo;
-}
 
 // One CTA walks kLocItems*kLocateThreads consecutive points.  Histogram updates go to
 // a small shared-memory table (bin -> count) first, so the global bin counters see one
@@ -79,7 +47,8 @@ __device__ __forceinline__ int table_slot(int *s_bin, int bin) {
 // for the lanes that miss.  Departure points arrive in leaf-major order, so nearly all hit.
 template <bool MULTI, bool BOXES>
 __global__ void __launch_bounds__(kLocateThreads)
-locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes, int n_leaf, int periodic,
+locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes,
+              const uint32_t *__restrict__ cells, int cell_shift, int n_leaf, int periodic,
               double *__restrict__ pos, size_t n, int32_t *__restrict__ leaf_out,
               uint32_t *__restrict__ rank_out, uint32_t *__restrict__ count,
               const uint64_t *__restrict__ splitters, int nranks, int myrank) {
@@ -160,9 +129,11 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
     uint32_t rank = 0;
     bool todo = valid;
 
+    int n_hit = 0;  // lanes the remembered leaf resolved
     if (BOXES && guess >= 0) {  // warp-uniform
       const bool hit = todo && in && ((((ix ^ gbox.x) | (iy ^ gbox.y) | (iz ^ gbox.z)) >> gbox.w) == 0u);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
+      n_hit = __popc(m);
       if (m) {
         const int claimer = __ffs(m) - 1;
         if (gslot == -2) {  // first hit on this guess: find its row of the CTA table once
@@ -219,47 +190,29 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
         }
       }
 
-      // Warp-cooperative phase: the lanes of a warp mostly share the leaf of the first
-      // unresolved lane.  Without boxes the previous batch's leaf is tried first by key range.
-      unsigned pending = __ballot_sync(0xffffffffu, todo);
-      for (int c = BOXES ? 1 : 0; c < kCoopIters + 1 && pending; c++) {
-        const int leader = __ffs(pending) - 1;
-        const uint64_t lk = __shfl_sync(0xffffffffu, key, leader);
-        int j;
-        if (c == 0) {
-          if (guess < 0) continue;
-          j = guess;
+      // Per-lane lookup: the cell table gives the range of leaves that can hold the key (count of
+      // leaf keys <= first key of the cell, and of the next cell), a short binary search finishes
+      // (<= 3 steps when the leaves are at most one level finer than the table).
+      int j = -1, n_new = 0;
+      if (todo) {
+        if (key == ~0ull) {
+          j = n_leaf - 1;  // saturated key: after every leaf key
         } else {
-          j = warp_count_le(keys, n_leaf, lk, lane) - 1;  // warp-uniform
-          guess = j;
-          gslot = -2;
-          if (BOXES && j >= 0) gbox = __ldg(boxes + j);
-        }
-        const uint64_t klo = (j >= 0) ? __ldg(keys + j) : 0ull;
-        const bool last = (j + 1 >= n_leaf);
-        const uint64_t khi = last ? ~0ull : __ldg(keys + j + 1);
-        const bool hit = ((pending >> lane) & 1u) && key >= klo && (last || key < khi);
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (m) {  // warp-uniform
-          const int b = (j >= 0) ? j : n_leaf;
-          const int claimer = __ffs(m) - 1;
-          int sl = -1;
-          uint32_t base = 0;
-          claim(b, m, claimer, sl, base);
-          sl = __shfl_sync(0xffffffffu, sl, claimer);
-          base = __shfl_sync(0xffffffffu, base, claimer);
-          if (hit) {
-            bin = b;
-            slot = sl;
-            rank = base + __popc(m & lt);
+          const unsigned c = (unsigned)(key >> cell_shift);
+          int lo = (int)__ldg(cells + c), hi = (int)__ldg(cells + c + 1);
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(keys + mid) <= key)
+              lo = mid + 1;
+            else
+              hi = mid;
           }
-          pending &= ~m;
+          j = lo - 1;
         }
-        if (c > 0 && __popc(m) < 4) break;  // incoherent input: stop paying for warp-wide searches
-      }
-      if ((pending >> lane) & 1u) {  // per-lane fallback, updates aggregated per leaf
-        const int j = lane_count_le(keys, n_leaf, key) - 1;
         bin = (j >= 0) ? j : n_leaf;
+      }
+      const unsigned pending = __ballot_sync(0xffffffffu, todo);
+      if (todo) {  // one table (or global) update per distinct leaf among the pending lanes
         const unsigned peers = __match_any_sync(pending, bin);
         const int leader = __ffs(peers) - 1;
         int sl = -1;
@@ -267,6 +220,15 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
         claim(bin, peers, leader, sl, base);
         slot = __shfl_sync(peers, sl, leader);
         rank = __shfl_sync(peers, base, leader) + __popc(peers & lt);
+        n_new = (j >= 0) ? __popc(peers) : 0;
+      }
+      // the leaf that took the most lanes becomes the next batch's guess, unless the old guess
+      // still holds more of the warp
+      const unsigned best = __reduce_max_sync(0xffffffffu, ((unsigned)n_new << 8) | (unsigned)(31 - lane));
+      if ((int)(best >> 8) > n_hit) {
+        guess = __shfl_sync(0xffffffffu, bin, 31 - (int)(best & 0xffu));
+        gslot = -2;
+        if (BOXES) gbox = __ldg(boxes + guess);
       }
     }
     if (valid) {
@@ -307,7 +269,8 @@ int launch_locate(tbslas_ctx *ctx, const LocateArgs &a) {
     return fail(ctx, TBSLAS_ERR_INVALID, "send counts must follow the leaf bins");
 #define TB_LOCATE(M, B)                                                                          \
   locate_kernel<M, B><<<grid, kLocateThreads, 0, ctx->stream>>>(                                 \
-      t->d_key, t->d_box, (int)t->n_leaf, a.periodic, a.pos, a.n, a.leaf, a.rank, a.count,       \
+      t->d_key, t->d_box, t->d_cell, t->cell_shift, (int)t->n_leaf, a.periodic, a.pos, a.n,      \
+      a.leaf, a.rank, a.count,                                                                   \
       multi ? t->d_splitters : nullptr, multi ? ctx->nranks : 1, multi ? ctx->rank : 0)
   if (multi) {
     if (boxes) TB_LOCATE(true, true); else TB_LOCATE(true, false);
