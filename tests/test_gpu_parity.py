@@ -216,6 +216,46 @@ def test_gpu_locate_faces_corners_and_leaf_major_streams(ctx, port, bc):
         assert rel_err(v, vo) < RTOL
 
 
+@pytest.mark.parametrize("case", ["root", "depth1", "deep_line", "deep_line_shard", "random"])
+def test_gpu_locate_tree_shapes(ctx, port, case):
+    """The cell table of the locate kernel against the oracle on tree shapes that
+    stress it: leaves coarser than the table cells (a single root leaf), leaves many levels
+    finer than the cells (a needle refined to depth 11: long ranges per cell), a shard of it
+    (keys before the first and after the last local leaf), and randomly refined trees."""
+    api = _api()
+    rng = np.random.default_rng({"root": 1, "depth1": 2, "deep_line": 3, "deep_line_shard": 4, "random": 5}[case])
+    if case == "root":
+        coord, dd = np.zeros((1, 3)), np.zeros(1, dtype=np.uint8)
+    elif case == "depth1":
+        coord, dd = ftm.uniform_leaves(1)
+    elif case in ("deep_line", "deep_line_shard"):
+        def refine(lower, edge, d):  # cells cut by the segment x = y = z near 0.3..0.31
+            lo, hi = lower, lower + edge[:, None]
+            return np.all((lo <= 0.31) & (hi >= 0.3), axis=1)
+        coord, dd = ftm.adaptive_leaves(refine, 1, 11)
+    else:
+        def refine(lower, edge, d):
+            return rng.random(lower.shape[0]) < 0.45
+        coord, dd = ftm.adaptive_leaves(refine, 1, 7)
+    ft = ftm.random_tree(coord, dd, 3, 2, seed=17)
+    if case == "deep_line_shard":
+        ft = ft.shard(ft.n_leaf // 3, 2 * ft.n_leaf // 3)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    size = np.power(0.5, ft.depth.astype(np.float64))
+    pick = rng.integers(0, ft.n_leaf, size=30000)
+    inside = ft.coord[pick] + size[pick, None] * rng.random((30000, 3))        # leaf-weighted
+    pts = np.concatenate([rng.uniform(-0.05, 1.05, size=(30000, 3)), inside,
+                          ft.coord[pick[:5000]], ft.coord[pick[:5000]] + size[pick[:5000], None]])
+    for bc in (0, 1):
+        vo, lo, po = port.eval_tree(h, 2, pts, bc)
+        pos = pts.copy()
+        v, leaf = f.eval_with_leaf(pos, bc)
+        assert np.array_equal(leaf, lo)
+        assert np.array_equal(pos, po)
+        assert rel_err(v, vo) < RTOL or np.abs(vo).max() == 0
+
+
 def test_gpu_locate_overlapping_leaves_fall_back_to_keys(ctx, port):
     """A leaf list that is NOT a set of disjoint octants (a depth-2 octant listed next to the
     depth-1 octant that contains it): 'inside the box' no longer implies 'last leaf with key <=
