@@ -49,21 +49,27 @@ refit_gemm_kernel(const double *__restrict__ vals, const double *__restrict__ Mp
   const long long row0 = (long long)blockIdx.y * kBM;
   const int col0 = blockIdx.x * kBN;
 
-  // A loader: thread -> (row = tid / 2, 8 consecutive k); B loader: (k = tid / 16, 4 consecutive n)
-  const int ar = tid >> 1, ak = (tid & 1) * 8;
-  const long long arow = row0 + ar;
-  const bool arow_ok = arow < rows;
-  const double *abase = vals;
-  if (arow_ok) abase = vals + (arow / dof) * (long long)P * dof + (arow % dof) * (long long)sd;
+  // A loader: thread -> (rows tid / 16 + 16 i, i = 0..7; k = tid % 16): the 16 lanes of a half-warp
+  // fetch the 128 contiguous bytes of one row of the tile (rows are only 8-byte aligned, hence
+  // 8-byte cp.async), so an instruction touches 2 rows x 4-5 sectors instead of 32 scattered ones.
+  // B loader: (k = tid / 16, 4 consecutive n)
+  const int ar = tid >> 4, ak = tid & 15;
+  const double *abase[8];
+  bool arow_ok[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const long long arow = row0 + ar + 16 * i;
+    arow_ok[i] = arow < rows;
+    abase[i] = arow_ok[i] ? vals + (arow / dof) * (long long)P * dof + (arow % dof) * (long long)sd : vals;
+  }
   const int bk = tid >> 4, bn = (tid & 15) * 4;
   auto load_tiles = [&](int kt, int buf) {
     const int k0 = kt * kBK;
-    double *a_dst = As + (buf * kBM + ar) * kAp + ak;
+    const int k = k0 + ak;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const int k = k0 + ak + i;
-      const bool ok = arow_ok && k < P;
-      cp8(a_dst + i, abase + (ok ? (long long)k * sk : 0), ok);
+      const bool ok = arow_ok[i] && k < P;
+      cp8(As + (buf * kBM + ar + 16 * i) * kAp + ak, abase[i] + (ok ? (long long)k * sk : 0), ok);
     }
     cp16(Bs + (buf * kBK + bk) * kBp + bn, Mp + (size_t)(k0 + bk) * Np + col0 + bn);
     cp16(Bs + (buf * kBK + bk) * kBp + bn + 2, Mp + (size_t)(k0 + bk) * Np + col0 + bn + 2);
