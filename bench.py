@@ -11,16 +11,19 @@ semilag.inc:27-45 -> traj.inc:49-68 -> tree_functor.h:397-690).
 
 Default workload = BASELINE.json configs[1] ("c2": Zalesak slotted sphere, adaptive octree,
 degree 14, max depth 7, 81 348 leaves, 274.5 M arrival points).  Prints ONE JSON line:
-`value` = points/s with inputs resident in HBM; `e2e` = the same through the C ABI with
-pinned HOST buffers (H2D of the arrival points and D2H of the values inside the timed
-region); `roofline` for the dominant kernel (Chebyshev evaluation, FP64-pipe bound) from
-CUDA events recorded around every launch during the timed region; `cpu_baseline` = the
-reference's own code (oracle/_ref) on this host's cores over a bounded sample.
+`value` = points/s with inputs resident in HBM; `e2e` = the same step through the C ABI with
+pinned HOST buffers -- the tree-level call a reference driver makes (SolveSemilagInSitu:
+coefficients up, arrival points generated in HBM, values down; `e2e.point_array_call` is the
+SolveSemilagRK2 flavour with 24 B/point of arrival points over PCIe); `semilag_step` = the whole
+tree-level step incl. the refit, on the device; `roofline` for the dominant kernel (Chebyshev
+evaluation, FP64-pipe bound) from CUDA events recorded around every launch during the timed
+region; `cpu_baseline` = the reference's own code (oracle/_ref) on this host's cores over a
+bounded sample.
 
 Multi-GPU (torchrun, one rank per GPU): the advected tree is split into equal contiguous
-Morton ranges, the velocity tree is co-partitioned with the same split keys, and foreign
-departure points travel by NCCL all-to-all-v inside the library; total work is fixed
-("scaling": "strong").
+Morton ranges and foreign departure points travel by NCCL all-to-all-v inside the library; a
+velocity tree of at most 1 GiB is held whole by every rank (--shard-velocity: co-partitioned
+with the same split keys, the reference's layout); total work is fixed ("scaling": "strong").
 """
 from __future__ import annotations
 

@@ -45,6 +45,8 @@ __device__ __forceinline__ int table_slot(int *s_bin, int bin) {
 // compare on the depth-15 anchors floor(c * 2^15); inside the box implies "last leaf with
 // key <= key(point)", so the Morton key is only interleaved, and the leaf list only searched,
 // for the lanes that miss.  Departure points arrive in leaf-major order, so nearly all hit.
+// Slow path: per-lane lookup of the key in the tree's cell table (number of leaf keys <= the first
+// key of every cell of a uniform depth-g grid) + a binary search over the few leaves of that cell.
 template <bool MULTI, bool BOXES>
 __global__ void __launch_bounds__(kLocateThreads)
 locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes,
