@@ -421,7 +421,11 @@ def run_b200(args):
     # ---- roofline of the dominant kernel -----------------------------------------------
     hbm_peak, hbm_src = load_peaks()
     ev = prof["ChebEval"]
-    n_eval_vel = 2 * len(tvel)
+    # dof-3 launches of a step: 2 per RK stage pair when the snapshots' coefficients are combined in
+    # time (one evaluation per stage), 2 * len(tvel) when every snapshot is evaluated
+    combined = len(tvel) > 1 and all(np.array_equal(v.keys(), wl.vel[0].keys()) and
+                                     np.array_equal(v.depth, wl.vel[0].depth) for v in wl.vel)
+    n_eval_vel = 2 if (len(tvel) == 1 or combined) else 2 * len(tvel)
     # algorithmic work per launch, summed over the launches of the timed region
     P = (wl.q + 1) ** 3
     flops = args.steps * n_local * (n_eval_vel * workloads.flops_per_point_eval(wl.q, 3)
@@ -458,6 +462,10 @@ def run_b200(args):
                    "points_total": n_total, "points_per_gpu": n_local, "q": wl.q,
                    "bc": "periodic" if wl.bc else "freespace", "dt": wl.dt, "nrk": 1,
                    "velocity_trees": len(tvel), "velocity_leaves": wl.vel[0].n_leaf,
+                   "velocity_evaluations_per_step": n_eval_vel,
+                   "time_interpolation": None if not combined else
+                   "coefficients of the 4 snapshots (one leaf list) combined in time on the device, one "
+                   "evaluation per RK stage; tbslas_b200_set_time_combine(ctx, 0) evaluates every snapshot",
                    "l2_policy": "inputs (%.1f GB of points per step) exceed the 126 MB L2" %
                                 (n_local * 24 / 1e9),
                    "partition": "single GPU" if world == 1 else

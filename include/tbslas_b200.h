@@ -140,6 +140,15 @@ int tbslas_b200_eval_set4(tbslas_tree *const trees[4], const double times[4], do
 /* FieldExtrapFunctor::operator() (tree_extrap_functor.h:47-78). */
 int tbslas_b200_eval_extrap(tbslas_tree *tp, tbslas_tree *tc, int bc, double *pos,
                             size_t n, double *out, int mem);
+/* How SET4 / EXTRAP fields are evaluated when their trees share one leaf list (the usual case:
+ * snapshots of one adaptive tree).  mode 1 (default): the trees' coefficients are combined in
+ * time on the device and the field is evaluated ONCE -- sum_k w_k tree_k(x) is linear in the
+ * coefficients -- so 4 (2) tree evaluations, their point locations and, across ranks, their
+ * point exchanges become one; values agree with the reference's order of operations to
+ * rounding (~1e-15 of the field scale).  mode 0: every tree is evaluated and the values are
+ * combined per point exactly as tree_set_functor.h:55-72 / tree_extrap_functor.h:59-77 do.
+ * Trees with different leaf lists always take the mode-0 route. */
+int tbslas_b200_set_time_combine(tbslas_ctx *ctx, int mode);
 /* Any field kind through one entry point (t is ignored by STEADY and EXTRAP). */
 int tbslas_b200_eval_field(const tbslas_field *f, double t, int bc, double *pos, size_t n,
                            double *out, int mem);

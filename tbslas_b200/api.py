@@ -83,6 +83,12 @@ class Context:
             stream = stream.cuda_stream or 1  # torch's default stream is handle 0 = cudaStreamLegacy (1)
         self.check(self.lib.tbslas_b200_set_stream(self.h, stream))
 
+    def set_time_combine(self, on: bool) -> None:
+        """FieldSetFunctor/FieldExtrapFunctor over trees with one leaf list: combine the
+        coefficients in time and evaluate once (True, default) or evaluate every tree and combine
+        the values per point in the reference's order (False)."""
+        self.check(self.lib.tbslas_b200_set_time_combine(self.h, int(bool(on))))
+
     def synchronize(self) -> None:
         self.check(self.lib.tbslas_b200_synchronize(self.h))
 

@@ -83,6 +83,44 @@ int launch_cubic_time(tbslas_ctx *ctx, const double *v4, size_t m, const double 
   return TBSLAS_OK;
 }
 
+// Hermite-in-time weights of the four snapshots: InterpCubic1D (cubic.h:36-56) is linear in
+// p0..p3, out = w0 p0 + w1 p1 + w2 p2 + w3 p3 with the w's below (host arithmetic).
+void cubic_time_weights(const double times[4], double t, double w[4]) {
+  const double d10 = times[1] - times[0], d21 = times[2] - times[1], d32 = times[3] - times[2];
+  const double tt = (t - times[1]) / d21, t2 = tt * tt, t3 = t2 * tt;
+  const double h00 = 2 * t3 - 3 * t2 + 1, h10 = t3 - 2 * t2 + tt, h01 = -2 * t3 + 3 * t2, h11 = t3 - t2;
+  const double H10 = h10 * d21, H11 = h11 * d21;  // multiply the tangents m1, m2
+  // m1 = (p2-p1)*0.5/d21 + (p1-p0)*0.5/d10,  m2 = (p3-p2)*0.5/d32 + (p2-p1)*0.5/d21
+  w[0] = -H10 * 0.5 / d10;
+  w[1] = h00 + H10 * (0.5 / d10 - 0.5 / d21) - H11 * 0.5 / d21;
+  w[2] = h01 + H10 * 0.5 / d21 + H11 * (0.5 / d21 - 0.5 / d32);
+  w[3] = H11 * 0.5 / d32;
+}
+
+// Coefficients of the field  sum_k w_k * tree_k  for trees that share their leaf list: the
+// evaluation is linear in the coefficients, so ONE evaluation of the combined block replaces
+// one evaluation per tree followed by a per-point combination.
+__global__ void combine_coeff_kernel(const double *__restrict__ c0, const double *__restrict__ c1,
+                                     const double *__restrict__ c2, const double *__restrict__ c3,
+                                     double w0, double w1, double w2, double w3, int n_tree, size_t m,
+                                     double *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double v = __dadd_rn(__dmul_rn(w0, c0[i]), __dmul_rn(w1, c1[i]));
+  if (n_tree == 4) v = __dadd_rn(__dadd_rn(v, __dmul_rn(w2, c2[i])), __dmul_rn(w3, c3[i]));
+  out[i] = v;
+}
+
+int launch_combine_coeff(tbslas_ctx *ctx, const double *const c[4], const double w[4], int n_tree, size_t m,
+                         double *out) {
+  StageScope sc(ctx, ST_COMBINE, (double)m, 1);
+  if (!m) return TBSLAS_OK;
+  combine_coeff_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(
+      c[0], c[1], n_tree == 4 ? c[2] : c[0], n_tree == 4 ? c[3] : c[0], w[0], w[1], w[2], w[3], n_tree, m, out);
+  TB_CUDA(ctx, cudaGetLastError());
+  return TBSLAS_OK;
+}
+
 // tbslas::FieldExtrapFunctor (reference src/tree/tree_extrap_functor.h:70-77):
 // out = 1.5*vc - 0.5*vp.
 template <bool AXPY>

@@ -65,6 +65,7 @@ enum Slot {
   WS_RECVLEAF,   // int32 leaf ids of received points / returned to the origin
   WS_RETLEAF,
   WS_MISC,
+  WS_COEF,       // coefficients of a field combined in time (FieldSetFunctor / FieldExtrapFunctor)
   WS_COUNT_SLOTS
 };
 
@@ -106,6 +107,10 @@ struct tbslas_ctx {
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_pipe[5][2] = {};  // [in, phaseA, pos_out, phaseB, out][buffer parity]
   tb::Pt2Coeff pt2coeff[TBSLAS_MAX_CHEB_DEG + 1];
+  // FieldSetFunctor / FieldExtrapFunctor over trees with one leaf list: 1 = combine the trees'
+  // coefficients in time and evaluate once (default), 0 = evaluate every tree and combine the
+  // values per point, in the reference's order (tree_set_functor.h:55-72)
+  int time_combine = 1;
   // pinned host scratch for small device->host reads (exchange counts: [nranks][nranks])
   unsigned *h_counts = nullptr;
 };
@@ -226,6 +231,9 @@ int launch_cubic_time(tbslas_ctx *ctx, const double *v4 /*[4][m]*/, size_t m, co
                       double t, double *out, const double *base, double alpha, int axpy);
 int launch_extrap(tbslas_ctx *ctx, const double *vc, const double *vp, size_t m, double *out,
                   const double *base, double alpha, int axpy);
+void cubic_time_weights(const double times[4], double t, double w[4]);
+int launch_combine_coeff(tbslas_ctx *ctx, const double *const c[4], const double w[4], int n_tree, size_t m,
+                         double *out);
 int launch_axpy(tbslas_ctx *ctx, const double *base, const double *v, double alpha, size_t m,
                 double *out);
 int launch_keep_counts(tbslas_ctx *ctx, const uint32_t *count, uint32_t *keep, size_t n_leaf, bool add);

@@ -83,6 +83,8 @@ def test_config3_time_varying_full_size(ctx):
         n = pos.shape[0]
         fset = api.FieldSetFunctor(tv, wl.vel_times)
         tq = 0.3 * wl.dt
+        vc = fset(pos.clone(), time=tq, bc=1)   # default: coefficients combined in time, one evaluation
+        ctx.set_time_combine(False)              # the reference's order: 4 evaluations + InterpCubic1D
         v = fset(pos.clone(), time=tq, bc=1)
         # the same from four single-tree evaluations + InterpCubic1D (cubic.h:28-56) in torch,
         # same operation order, un-fused: bit-exact
@@ -98,15 +100,21 @@ def test_config3_time_varying_full_size(ctx):
         want = h00 * p4[1] + (h10 * (t2 - t1)) * m1 + h01 * p4[2] + (h11 * (t2 - t1)) * m2
         torch.cuda.synchronize()
         assert float((v - want).abs().max()) <= 1e-15 * float(want.abs().max())
+        # ... and the one-evaluation route agrees with it to rounding
+        assert float((vc - want).abs().max()) <= 1e-13 * float(want.abs().max())
         # equal snapshots -> identity in time
         same = api.FieldSetFunctor([tv[1]] * 4, wl.vel_times)
         v1 = same(pos.clone(), time=tq, bc=1)
         assert float((v1 - p4[1]).abs().max()) <= 4e-16 * float(p4[1].abs().max())
+        ctx.set_time_combine(True)
+        v1c = same(pos.clone(), time=tq, bc=1)
+        assert float((v1c - p4[1]).abs().max()) <= 1e-13 * float(p4[1].abs().max())
         # the full step runs and is finite at this size
         out = api.SolveSemilagRK2(fset, api.NodeFieldFunctor(tcon), pos, 1, wl.dt, 1, 1)
         torch.cuda.synchronize()
         assert bool(torch.isfinite(out).all()) and out.shape == (n, 1)
     finally:
+        ctx.set_time_combine(True)
         ctx.set_stream(None)
         tcon.destroy()
         for t in tv:

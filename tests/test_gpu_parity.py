@@ -90,7 +90,10 @@ def test_gpu_golden_timevarying(ctx):
     fset = api.FieldSetFunctor(trees, g["times"].tolist())
     fext = api.FieldExtrapFunctor(trees[0], trees[1])
     fcur = api.NodeFieldFunctor(trees[1])
-    for bc in (0, 1):
+    for bc, combine in ((0, True), (1, True), (0, False), (1, False)):
+        # combine: coefficients interpolated in time + one evaluation (default); else every
+        # snapshot is evaluated and the values are combined per point, in the reference's order
+        ctx.set_time_combine(combine)
         v = fset(g["pts"].copy(), time=float(g["tq"]), bc=bc)
         assert rel_err(v, g["set4_bc%d" % bc]) < RTOL
         e = fext(g["pts"].copy(), bc=bc)
@@ -99,6 +102,14 @@ def test_gpu_golden_timevarying(ctx):
         assert np.abs(x - g["traj_set4_bc%d" % bc]).max() < RTOL
         x = api.ComputeTrajRK2(fcur, g["pts"], 0.1, 0.0, 1, bc, extrap_fn=fext)
         assert np.abs(x - g["traj_extrap_bc%d" % bc]).max() < RTOL
+    ctx.set_time_combine(True)
+    # snapshots on DIFFERENT leaf lists cannot be combined: they take the per-tree route
+    c2, d2 = ftm.uniform_leaves(2)
+    other = ctx.tree(ftm.random_tree(c2, d2, int(g["q"]), int(g["dof"]), seed=3))
+    mixed = api.FieldExtrapFunctor(trees[0], other)
+    pts = g["pts"].copy()
+    want = 1.5 * api.NodeFieldFunctor(other)(pts.copy(), bc=1) - 0.5 * api.NodeFieldFunctor(trees[0])(pts.copy(), bc=1)
+    assert rel_err(mixed(pts.copy(), bc=1), want) < RTOL
 
 
 def test_gpu_golden_cubic_grid(ctx):
