@@ -286,6 +286,14 @@ def run_b200(args):
     n_total = wl.n_points
 
     def step_dev():
+        # the tree-level step on device buffers: steps (1)+(2) of tbslas::SolveSemilagInSitu --
+        # arrival points generated in HBM from the advected tree's leaves, RK2 trajectories, the
+        # scalar at the departure points -> vals (HBM)
+        ctx.check(ctx.lib.tbslas_b200_semilag_insitu(
+            api.C.byref(vel_f.field), None, tcon.h, wl.bc, 1, float(wl.dt), 1, vals.data_ptr(), 1))
+
+    def step_points():
+        # the same on an explicit point array (tbslas::SolveSemilagRK2): no structure to exploit
         api.SolveSemilagRK2(vel_f, con_f, pos, 1, wl.dt, 1, wl.bc, points_vals=vals)
 
     def barrier():
@@ -335,6 +343,24 @@ def run_b200(args):
         per_rank = gathered
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
+    m_exc = ctx.last_grid_exceptions()
+
+    # the point-array flavour of the same step, device resident (what `value` was before the
+    # tree-level call learnt to use the tensor structure of the arrival points)
+    step_points()
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_pts_steps = max(1, min(args.steps, 3))
+    p0.record()
+    for _ in range(n_pts_steps):
+        step_points()
+    p1.record()
+    barrier()
+    pts_ms = p0.elapsed_time(p1) / n_pts_steps
+    if world > 1:
+        t = torch.tensor([pts_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pts_ms = float(t.item())
 
     # ---- the other half of the metric: semi-Lagrangian step time of the tree-level call ---
     # tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) entirely on the device: arrival points
@@ -426,12 +452,18 @@ def run_b200(args):
     combined = len(tvel) > 1 and all(np.array_equal(v.keys(), wl.vel[0].keys()) and
                                      np.array_equal(v.depth, wl.vel[0].depth) for v in wl.vel)
     n_eval_vel = 2 if (len(tvel) == 1 or combined) else 2 * len(tvel)
+    tensor = ("TensorGrid" in prof and prof["TensorGrid"]["ms"] > 0)
+    if tensor:  # the first velocity evaluation ran by sum factorisation; only its exceptions
+        n_eval_vel -= 1  # (m_exc points) went through the Chebyshev kernel
     # algorithmic work per launch, summed over the launches of the timed region
     P = (wl.q + 1) ** 3
-    flops = args.steps * n_local * (n_eval_vel * workloads.flops_per_point_eval(wl.q, 3)
-                                    + workloads.flops_per_point_eval(wl.q, 1))
+    n_exc = m_exc if tensor else 0
+    flops = args.steps * (n_local * (n_eval_vel * workloads.flops_per_point_eval(wl.q, 3)
+                                     + workloads.flops_per_point_eval(wl.q, 1))
+                          + n_exc * workloads.flops_per_point_eval(wl.q, 3))
     coef_bytes = 8.0 * ftm.ncoef(wl.q) / P
-    bytes_alg = args.steps * n_local * (n_eval_vel * (24 + 24 + 3 * coef_bytes) + (24 + 8 + coef_bytes))
+    bytes_alg = args.steps * (n_local * (n_eval_vel * (24 + 24 + 3 * coef_bytes) + (24 + 8 + coef_bytes))
+                              + n_exc * (24 + 24 + 3 * coef_bytes))
     ach_tf = flops / (ev["ms"] * 1e-3) * 1e-12 if ev["ms"] > 0 else 0.0
     ach_gbs = bytes_alg / (ev["ms"] * 1e-3) * 1e-9 if ev["ms"] > 0 else 0.0
     stage_ms = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if v["ms"] > 0}
@@ -462,7 +494,12 @@ def run_b200(args):
                    "points_total": n_total, "points_per_gpu": n_local, "q": wl.q,
                    "bc": "periodic" if wl.bc else "freespace", "dt": wl.dt, "nrk": 1,
                    "velocity_trees": len(tvel), "velocity_leaves": wl.vel[0].n_leaf,
-                   "velocity_evaluations_per_step": n_eval_vel,
+                   "step": "tbslas_b200_semilag_insitu on device buffers: arrival points generated in HBM, "
+                           "RK2 trajectories, scalar at the departure points",
+                   "velocity_evaluations_per_step": n_eval_vel + (1 if tensor else 0),
+                   "first_velocity_evaluation": None if not tensor else
+                   "sum factorisation over the arrival grids (tensor_eval.cu); %d of %d points per step "
+                   "(on velocity-leaf faces) through the generic kernels" % (n_exc, n_local),
                    "time_interpolation": None if not combined else
                    "coefficients of the 4 snapshots (one leaf list) combined in time on the device, one "
                    "evaluation per RK stage; tbslas_b200_set_time_combine(ctx, 0) evaluates every snapshot",
@@ -494,6 +531,9 @@ def run_b200(args):
                             "arrays: arrival points in (24 B/point over PCIe), advected values out; "
                             "chunks pipelined over three streams"}},
         "roofline": roofline,
+        "value_point_array": {"value": n_total / (pts_ms * 1e-3), "unit": "points/s", "ms_per_step": pts_ms,
+                              "what": "the same step through tbslas_b200_semilag_rk2 (SolveSemilagRK2) on an "
+                                      "explicit, HBM-resident point array: all three evaluations point by point"},
         "semilag_step": {"ms": step_ms, "what": "SolveSemilagInSitu on the device: arrival-point generation "
                          "+ RK2 trajectories + scalar evaluation + values->coefficients refit, "
                          "coefficients stay in HBM (tree_semilag.h:92-135)"},

@@ -169,6 +169,18 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2,
                             int timestep, double dt, int nrk, double *out_vals,
                             double *out_dep, int mem);
 
+/* Tree-level calls (semilag_insitu, semilag_insitu_update) know that the arrival points are the
+ * (q+1)^3 tensor grids of con's leaves.  mode 1 (default): where such a leaf lies inside one leaf
+ * of a dof-3 velocity tree held on this rank, the FIRST velocity evaluation of the step runs by
+ * sum factorisation (three 1-D passes per leaf: 88 k instead of 2.75 M FMA per leaf and component
+ * at q = 14) -- the same polynomial at the same points summed in another order, ~1e-15 of the field
+ * scale; grid points on a velocity-leaf face, and leaves not inside one velocity leaf, take the
+ * generic path, so every point is evaluated by the leaf the reference assigns it to.  mode 0:
+ * every evaluation is point by point. */
+int tbslas_b200_set_tensor_grid(tbslas_ctx *ctx, int mode);
+/* Arrival points of the most recent tree-level call (or of its last chunk, for host buffers) that
+ * took the generic path instead (on a velocity-leaf face, or in a leaf not inside one velocity leaf). */
+int tbslas_b200_last_grid_exceptions(tbslas_ctx *ctx, size_t *n);
 /* Steps (1)+(2) of tbslas::SolveSemilagInSitu (tree_semilag.h:92-130): the arrival points
  * are the Chebyshev grid points of `con`'s own (local) leaves, generated in HBM
  * (CollectChebTreeGridPoints, tree_utils.h:442-498) -- no 24 B/point host->device copy --

@@ -89,6 +89,16 @@ class Context:
         the values per point in the reference's order (False)."""
         self.check(self.lib.tbslas_b200_set_time_combine(self.h, int(bool(on))))
 
+    def set_tensor_grid(self, on: bool) -> None:
+        """Tree-level calls: evaluate the velocity at the arrival grids by sum factorisation
+        (True, default) or point by point (False)."""
+        self.check(self.lib.tbslas_b200_set_tensor_grid(self.h, int(bool(on))))
+
+    def last_grid_exceptions(self) -> int:
+        n = C.c_size_t()
+        self.check(self.lib.tbslas_b200_last_grid_exceptions(self.h, C.byref(n)))
+        return int(n.value)
+
     def synchronize(self) -> None:
         self.check(self.lib.tbslas_b200_synchronize(self.h))
 

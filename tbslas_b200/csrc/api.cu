@@ -83,7 +83,8 @@ static int prof_collect(tbslas_ctx *ctx) {
 
 static const char *kStageNames[ST_COUNT] = {"H2D",     "D2H",       "Locate", "Bin",
                                             "ChebEval", "Combine",   "CubicGrid", "Pack",
-                                            "Exchange", "Unpack",    "GridPoints", "Refit"};
+                                            "Exchange", "Unpack",    "GridPoints", "Refit",
+                                            "TensorGrid"};
 
 // multi-rank pieces (comm.cu)
 int comm_tree_splitters(tbslas_tree *t, uint64_t first_key);
@@ -216,6 +217,11 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   return TBSLAS_OK;
 }
 
+// used by tensor_eval.cu: the generic path for the arrival points its shortcut does not cover
+int eval_tree_dev_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out) {
+  return eval_local_points(t, bc, pos, n, EPI_STORE, out, nullptr, 0.0, nullptr, true);
+}
+
 // used by comm.cu to evaluate points received from other ranks (all of them local)
 int eval_received_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out,
                          int32_t *leaf_out) {
@@ -245,6 +251,46 @@ static int check_field(tbslas_ctx **ctx_out, const tbslas_field *f, int *dof) {
   return TBSLAS_OK;
 }
 
+// The ONE tree whose evaluation gives the field, if there is one: tree[0] of a steady field, or --
+// for SET4 / EXTRAP over trees with one leaf list -- a view of tree[0] with the coefficients
+// combined in time:  sum_k w_k eval(tree_k)(x) == eval(sum_k w_k coeff_k)(x), the evaluation being
+// linear in the coefficients and the leaf of x the same in every tree.  4 (resp. 2) evaluations,
+// their locate passes and, across ranks, their point exchanges become one; values agree with the
+// reference's order of operations to rounding (~1e-15 of the field scale).  *out = nullptr when
+// the field needs one evaluation per tree.
+static int field_single_tree(tbslas_ctx *ctx, const tbslas_field *f, double tq, tbslas_tree *view,
+                             tbslas_tree **out) {
+  *out = nullptr;
+  if (f->kind == TBSLAS_FIELD_STEADY) {  // time argument ignored, tree_functor.h:808-811
+    *out = f->tree[0];
+    return TBSLAS_OK;
+  }
+  const int nt = f->kind == TBSLAS_FIELD_SET4 ? 4 : 2;
+  bool one_list = ctx->time_combine != 0;
+  for (int i = 1; i < nt && one_list; i++)
+    one_list = same_leaves(f->tree[0], f->tree[i]) && f->tree[i]->replicated == f->tree[0]->replicated;
+  if (!one_list) return TBSLAS_OK;
+  tbslas_tree *t0 = f->tree[0];
+  double w[4] = {0, 0, 0, 0};
+  if (f->kind == TBSLAS_FIELD_SET4) {
+    cubic_time_weights(f->times, tq, w);
+  } else {  // tree[0] = previous, tree[1] = current: 1.5*current - 0.5*previous
+    w[0] = -0.5;
+    w[1] = 1.5;
+  }
+  const size_t mc = (t0->n_leaf + 1) * t0->stride;
+  void *cc;
+  TB_TRY(ws_get(ctx, WS_COEF, sizeof(double) * mc, &cc));
+  const double *src[4] = {f->tree[0]->d_coeff, f->tree[1]->d_coeff, nt == 4 ? f->tree[2]->d_coeff : nullptr,
+                          nt == 4 ? f->tree[3]->d_coeff : nullptr};
+  TB_TRY(launch_combine_coeff(ctx, src, w, nt, mc, (double *)cc));
+  if (t0->n_leaf && !t0->d_pt_count) TB_CUDA(ctx, cudaMalloc(&t0->d_pt_count, sizeof(uint32_t) * t0->n_leaf));
+  *view = *t0;  // same leaves, keys, boxes, splitters; combined coefficients
+  view->d_coeff = (double *)cc;
+  *out = view;
+  return TBSLAS_OK;
+}
+
 // out = field(pos)                       (axpy == 0)
 // out = base + alpha * field(pos)        (axpy == 1; the RK2 position update)
 static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos, size_t n,
@@ -252,42 +298,15 @@ static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos,
   tbslas_ctx *ctx;
   int dof;
   TB_TRY(check_field(&ctx, f, &dof));
-  if (f->kind == TBSLAS_FIELD_STEADY)  // time argument ignored, tree_functor.h:808-811
-    return eval_tree_dev(f->tree[0], bc, pos, n, axpy ? EPI_AXPY : EPI_STORE, out, base, alpha,
-                         nullptr);
-  const size_t m = n * dof;
-  void *va;
-  // Trees with one leaf list: the field is evaluated ONCE on coefficients combined in time --
-  // sum_k w_k eval(tree_k)(x) == eval(sum_k w_k coeff_k)(x), the evaluation being linear in the
-  // coefficients and the leaf of x the same in every tree.  4 (resp. 2) evaluations, their
-  // locate passes and, across ranks, their point exchanges become one; values agree with the
-  // reference's order of operations to rounding (~1e-15 of the field scale).
-  const int nt = f->kind == TBSLAS_FIELD_SET4 ? 4 : 2;
-  bool one_list = ctx->time_combine != 0;
-  for (int i = 1; i < nt && one_list; i++)
-    one_list = same_leaves(f->tree[0], f->tree[i]) && f->tree[i]->replicated == f->tree[0]->replicated;
-  if (one_list) {
-    tbslas_tree *t0 = f->tree[0];
-    double w[4] = {0, 0, 0, 0};
-    if (f->kind == TBSLAS_FIELD_SET4) {
-      cubic_time_weights(f->times, tq, w);
-    } else {  // tree[0] = previous, tree[1] = current: 1.5*current - 0.5*previous
-      w[0] = -0.5;
-      w[1] = 1.5;
-    }
-    const size_t mc = (t0->n_leaf + 1) * t0->stride;
-    void *cc;
-    TB_TRY(ws_get(ctx, WS_COEF, sizeof(double) * mc, &cc));
-    const double *src[4] = {f->tree[0]->d_coeff, f->tree[1]->d_coeff, nt == 4 ? f->tree[2]->d_coeff : nullptr,
-                            nt == 4 ? f->tree[3]->d_coeff : nullptr};
-    TB_TRY(launch_combine_coeff(ctx, src, w, nt, mc, (double *)cc));
-    if (t0->n_leaf && !t0->d_pt_count) TB_CUDA(ctx, cudaMalloc(&t0->d_pt_count, sizeof(uint32_t) * t0->n_leaf));
-    tbslas_tree view = *t0;  // same leaves, keys, boxes, splitters; combined coefficients
-    view.d_coeff = (double *)cc;
-    TB_TRY(eval_tree_dev(&view, bc, pos, n, axpy ? EPI_AXPY : EPI_STORE, out, base, alpha, nullptr));
-    t0->pt_count_valid = view.pt_count_valid;
+  tbslas_tree view, *one = nullptr;
+  TB_TRY(field_single_tree(ctx, f, tq, &view, &one));
+  if (one) {
+    TB_TRY(eval_tree_dev(one, bc, pos, n, axpy ? EPI_AXPY : EPI_STORE, out, base, alpha, nullptr));
+    if (one == &view) f->tree[0]->pt_count_valid = view.pt_count_valid;
     return TBSLAS_OK;
   }
+  const size_t m = n * dof;
+  void *va;
   if (f->kind == TBSLAS_FIELD_SET4) {  // tree_set_functor.h:55-72
     TB_TRY(ws_get(ctx, WS_VAL_A, sizeof(double) * 4 * m, &va));
     double *v4 = (double *)va;
@@ -309,9 +328,12 @@ static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos,
 // copy, traj.inc:57-64) or a separate read-only array, which saves the 48 B/point copy
 // xinit -> xsol -- only when the boundary is not periodic, because the periodic wrap rewrites the
 // evaluated positions in place (tree_functor.h:442-449) and the start array may be the caller's.
+// `grid` != nullptr: the start points are exactly the Chebyshev grid points of leaves [leaf0, ...)
+// of that tree (tree-level calls); the first velocity evaluation then runs by sum factorisation
+// (tensor_eval.cu) wherever that applies.
 static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, double *xsol,
                         double *xtmp, size_t n, double tinit, double tfinal, int nrk,
-                        const double *x0 = nullptr) {
+                        const double *x0 = nullptr, const tbslas_tree *grid = nullptr, size_t leaf0 = 0) {
   const double tau = (tfinal - tinit) / nrk;  // traj.inc:55
   double tcur = tinit;
   tbslas_ctx *ctx = f1->tree[0]->ctx;
@@ -323,7 +345,20 @@ static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, 
   for (int s = 0; s < nrk; s++) {
     double *x = (s == 0 && x0) ? const_cast<double *>(x0) : xsol;  // not written unless periodic
     // v1 = V(x, t);  xtmp = x + 0.5*tau*v1      traj.inc:33-36 (x wrapped in place if periodic)
-    TB_TRY(eval_field_dev(f1, tcur, bc, x, n, xtmp, 1, x, 0.5 * tau));
+    bool done = false;
+    if (s == 0 && grid && ctx->tensor_grid && x == xsol && n) {
+      const size_t P = (size_t)(grid->q + 1) * (grid->q + 1) * (grid->q + 1);
+      tbslas_tree view, *one = nullptr;
+      TB_TRY(field_single_tree(ctx, f1, tcur, &view, &one));
+      if (one && n % P == 0) {
+        const int rc = launch_tensor_grid_eval(ctx, one, grid, leaf0, n / P, bc, x, xtmp, 0.5 * tau);
+        if (rc == TBSLAS_OK)
+          done = true;
+        else if (rc != TBSLAS_ERR_UNSUPPORTED)
+          return rc;
+      }
+    }
+    if (!done) TB_TRY(eval_field_dev(f1, tcur, bc, x, n, xtmp, 1, x, 0.5 * tau));
     // v2 = V(xtmp, t + tau/2);  x = x + tau*v2  traj.inc:40-42
     TB_TRY(eval_field_dev(f2 ? f2 : f1, tcur + 0.5 * tau, bc, xtmp, n, xsol, 1, x, tau));
     tcur = tcur + tau;
@@ -391,7 +426,7 @@ struct PipeSpec {
 };
 enum { EV_IN = 0, EV_A, EV_POSOUT, EV_B, EV_OUT };
 
-static int pipe_chunks(tbslas_ctx *ctx, size_t n) {
+static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input) {
   static int forced = -1;
   if (forced < 0) {
     const char *e = getenv("TBSLAS_HOST_CHUNKS");
@@ -400,12 +435,15 @@ static int pipe_chunks(tbslas_ctx *ctx, size_t n) {
   if (forced > 0) return forced;
   if (ctx->nranks > 1) return 8;
   const size_t k = n >> 20;  // >= 1 Mi points per chunk
-  return (int)(k < 1 ? 1 : (k > 16 ? 16 : k));
+  // with host input the first chunk's copy is exposed, so chunks are small; without (tree-level
+  // calls) only the last chunk's copy-out is, and every chunk costs a host-visible count
+  const size_t kmax = has_input ? 16 : 8;
+  return (int)(k < 1 ? 1 : (k > kmax ? kmax : k));
 }
 
 template <class FA, class FB>
 static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA phase_a, FB phase_b) {
-  const int K = pipe_chunks(ctx, n);
+  const int K = pipe_chunks(ctx, n, sp.h_pos != nullptr);
   const size_t unit = sp.unit ? sp.unit : 1;
   const size_t chunk = ((n / unit + K - 1) / K) * unit + (n % unit ? unit : 0);
   PipeBufs bufs[2] = {};
@@ -545,6 +583,18 @@ int tbslas_b200_set_stream(tbslas_ctx *ctx, void *s) {
 int tbslas_b200_set_time_combine(tbslas_ctx *ctx, int mode) {
   if (!ctx || (mode != 0 && mode != 1)) return TBSLAS_ERR_INVALID;
   ctx->time_combine = mode;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_last_grid_exceptions(tbslas_ctx *ctx, size_t *n) {
+  if (!ctx || !n) return TBSLAS_ERR_INVALID;
+  *n = ctx->last_exceptions;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_set_tensor_grid(tbslas_ctx *ctx, int mode) {
+  if (!ctx || (mode != 0 && mode != 1)) return TBSLAS_ERR_INVALID;
+  ctx->tensor_grid = mode;
   return TBSLAS_OK;
 }
 
@@ -869,7 +919,7 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
         ctx, sp, n,
         [&](PipeBufs &B, size_t m, size_t off) {
           TB_TRY(launch_grid_points(ctx, con, B.pos, off / P, m / P));
-          return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk);
+          return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk, B.pos, con, off / P);
         },
         [&](PipeBufs &B, size_t m, size_t) { return eval_tree_dev(con, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, nullptr); });
   }
@@ -885,7 +935,7 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
     if (n) TB_TRY(launch_grid_points(ctx, con, (double *)xsol));
   }
   TB_TRY(traj_rk2_dev(f1, f2, bc, (double *)xsol, (double *)xtmp, n, tinit, tfinal, nrk,
-                      insitu ? (const double *)xsol : pos));
+                      insitu ? (const double *)xsol : pos, insitu ? con : nullptr, 0));
   if (mem == TBSLAS_MEM_DEVICE && out_dep && bc == TBSLAS_PERIODIC) {
     // keep the caller's departure points un-wrapped: evaluate on a copy
     TB_CUDA(ctx, cudaMemcpyAsync(xtmp, xsol, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice,

@@ -29,6 +29,7 @@ enum Stage {
   ST_UNPACK,
   ST_GRIDPTS,   // arrival point generation                (CollectChebTreeGridPoints)
   ST_REFIT,     // values -> coefficients GEMM              (SetTreeGridValues)
+  ST_TENSOR,    // velocity at the arrival grids by sum factorisation (tensor_eval.cu)
   ST_COUNT
 };
 
@@ -66,6 +67,10 @@ enum Slot {
   WS_RETLEAF,
   WS_MISC,
   WS_COEF,       // coefficients of a field combined in time (FieldSetFunctor / FieldExtrapFunctor)
+  WS_GRIDMAP,    // int32 [n_leaf] velocity leaf that contains each leaf of the advected tree
+  WS_EXC_IDX,    // uint32 [n] arrival points that need the generic evaluation
+  WS_EXC_POS,
+  WS_EXC_VAL,
   WS_COUNT_SLOTS
 };
 
@@ -111,6 +116,10 @@ struct tbslas_ctx {
   // coefficients in time and evaluate once (default), 0 = evaluate every tree and combine the
   // values per point, in the reference's order (tree_set_functor.h:55-72)
   int time_combine = 1;
+  // tree-level calls (semilag_insitu*): 1 = the velocity at the arrival grids is evaluated by sum
+  // factorisation (tensor_eval.cu), 0 = point by point like any other point set
+  int tensor_grid = 1;
+  size_t last_exceptions = 0;  // arrival points of the last such call that took the generic path
   // pinned host scratch for small device->host reads (exchange counts: [nranks][nranks])
   unsigned *h_counts = nullptr;
 };
@@ -248,6 +257,9 @@ void new_nodes_host(int q, double *x);  // tbslas::new_nodes 1-D table (host lib
 // refit.cu
 int set_pt2coeff(tbslas_ctx *ctx, int q, const double *M_host);
 int launch_refit(tbslas_ctx *ctx, tbslas_tree *t, const double *vals, int point_major);
+// tensor_eval.cu
+int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree *grid, size_t leaf0,
+                            size_t n_leaf, int bc, double *x, double *out, double alpha);
 // tailnorm.cu
 int launch_tail_norm(tbslas_ctx *ctx, const tbslas_tree *t, double *out);
 // peak.cu

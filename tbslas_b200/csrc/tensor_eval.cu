@@ -1,0 +1,458 @@
+// Velocity at the ARRIVAL points by sum factorisation.
+//
+// The first evaluation of a semi-Lagrangian step samples the velocity at the arrival points,
+// and in the tree-level call (tbslas::SolveSemilagInSitu, reference src/tree/tree_semilag.h:
+// 103-124) those are not arbitrary: they are the (q+1)^3 tensor grid of every leaf of the
+// advected tree (CollectChebTreeGridPoints, tree_utils.h:442-498).  Where such a leaf lies inside
+// ONE leaf of the velocity tree, the local coordinates of its grid are a tensor product too,
+//     xi(px) x eta(py) x zeta(pz),
+// and the triangular Chebyshev sum factorises into three 1-D passes
+//     A[i][j][px] = sum_k C[i][j][k] T_k(xi_px)            (120 rows x 15, <= 15 terms)
+//     B[i][py][px] = sum_j A[i][j][px] T_j(eta_py)          (15 x 225, <= 15 terms)
+//     u[pz][py][px] = sum_i B[i][py][px] T_i(zeta_pz)       (3375, 15 terms)
+// = 88 k FMA per leaf and component at q = 14 against 3375 x 815 = 2.75 M for point-by-point
+// evaluation (tree_functor.h:27-84): the same polynomial at the same points, summed in another
+// order (differences ~1e-15 of the field scale).  The coordinates and bases are formed exactly
+// as the generic kernels form them (same expressions, same rounding).
+//
+// Leaf assignment stays the reference's (tree_functor.h:190-198): a grid point belongs to the
+// velocity leaf that contains the leaf's box only if its depth-15 anchor lies inside that
+// leaf's integer box -- points ON an upper face belong to the neighbour (or wrap, or leave the
+// domain).  Those points, and all points of leaves that are not inside one velocity leaf, are
+// listed as EXCEPTIONS and evaluated by the generic locate/evaluate path afterwards.
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+#include "keys.cuh"
+
+namespace tb {
+
+constexpr int kTensorThreads = 256;
+constexpr int kMaxD = TBSLAS_MAX_CHEB_DEG + 1;
+constexpr int kMaxRows = kMaxD * (kMaxD + 1) / 2;
+
+struct TensorTables {
+  double node[kMaxD];          // tbslas::new_nodes, 1-D
+  uint16_t row_off[kMaxRows];  // first coefficient of row (i,j) in the packed block
+  uint16_t row_first[kMaxD + 1];  // first row of plane i
+};
+
+// grid leaf -> velocity leaf that contains its box, or -1
+__global__ void grid_leaf_map_kernel(const uint4 *__restrict__ gbox, size_t n_leaf,
+                                     const uint64_t *__restrict__ vkeys, const uint4 *__restrict__ vbox,
+                                     const uint32_t *__restrict__ vcell, int vshift, int v_nleaf,
+                                     int32_t *__restrict__ map) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_leaf) return;
+  const uint4 b = gbox[c];
+  const uint64_t key = anchor_key(b.x, b.y, b.z);
+  const unsigned cell = (unsigned)(key >> vshift);
+  int lo = (int)__ldg(vcell + cell), hi = (int)__ldg(vcell + cell + 1);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(vkeys + mid) <= key)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  const int j = lo - 1;
+  int r = -1;
+  if (j >= 0 && j < v_nleaf) {
+    const uint4 v = __ldg(vbox + j);
+    if (b.w <= v.w && ((((b.x ^ v.x) | (b.y ^ v.y) | (b.z ^ v.z)) >> v.w) == 0u)) r = j;
+  }
+  map[c] = r;
+}
+
+struct TensorParams {
+  const double *vcoeff;     // velocity coefficients, [leaf][dof][ncoef_pad]
+  const double4 *vgeom;
+  const uint4 *vbox;
+  unsigned vstride, ncoef_pad;
+  const double4 *ggeom;     // grid tree, already offset to the first leaf of the range
+  const uint8_t *gdepth;
+  const int32_t *map;
+  size_t n_leaf;
+  int d, periodic;
+  const double *x;          // [n_leaf * P][3] the grid points
+  double *out;              // [n_leaf * P][3] = x + alpha * v on regular points
+  double alpha;
+  unsigned *exc_count;      // exceptions: number and point ids
+  uint32_t *exc_idx;
+};
+
+__global__ void __launch_bounds__(kTensorThreads)
+tensor_grid_eval_kernel(const TensorParams p, const TensorTables tb_) {
+  extern __shared__ __align__(16) double sm[];
+  const int d = p.d, dp = d | 1, P2 = d * d, P = P2 * d, n_row = d * (d + 1) / 2;
+  double *sT = sm;                       // [3][d][dp]   T_k at the leaf's grid, per axis
+  double *sC = sT + 3 * d * dp;          // [ncoef_pad]
+  double *sA = sC + p.ncoef_pad;         // [n_row][dp]
+  double *sB = sA + n_row * dp;          // [d][P2]
+  __shared__ unsigned s_ok[3];           // bit i: node i of the axis lies inside the velocity leaf's box
+  __shared__ unsigned s_exc_base, s_exc_n;
+  const int t = threadIdx.x;
+  for (size_t leaf = blockIdx.x; leaf < p.n_leaf; leaf += gridDim.x) {
+    const int j = p.map[leaf];
+    const size_t gp0 = leaf * (size_t)P;
+    __syncthreads();  // previous leaf done with the shared arrays
+    if (t < 3) s_ok[t] = 0u;
+    if (t == 0) s_exc_n = 0u;
+    __syncthreads();
+    if (j >= 0 && t < 3 * d) {
+      const int a = t / d, i = t - a * d;
+      const double4 gc = p.ggeom[leaf], gv = p.vgeom[j];
+      const uint4 vb = p.vbox[j];
+      const double len = 1.0 / (double)(1u << p.gdepth[leaf]);
+      const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z), vc = a == 0 ? gv.x : (a == 1 ? gv.y : gv.z);
+      const unsigned vba = a == 0 ? vb.x : (a == 1 ? vb.y : vb.z);
+      const double x = __dadd_rn(c, __dmul_rn(len, tb_.node[i]));            // gridpts.cu
+      const double xi = __dadd_rn(__dmul_rn(__dsub_rn(x, vc), gv.w), -1.0);  // cheb_eval.cuh
+      const bool in = fabs(xi) <= 1.0;
+      const double xc = in ? xi : 0.0, x2 = 2.0 * xc;
+      double t0 = in ? 1.0 : 0.0, t1 = xc;
+      double *T = sT + a * d * dp + i;
+      T[0] = t0;
+      if (d > 1) T[dp] = t1;
+      for (int k = 2; k < d; k++) {
+        const double t2 = __dsub_rn(__dmul_rn(x2, t1), t0);
+        T[k * dp] = t2;
+        t0 = t1;
+        t1 = t2;
+      }
+      // anchor of the point along this axis (locate.cu): inside the velocity leaf's box?
+      const double xs = x * 32768.0;
+      int jx = __double2int_rd(xs);
+      if (!p.periodic && xs == 32768.0) jx = 32767;
+      if ((unsigned)jx < 32768u && ((((unsigned)jx ^ vba) >> vb.w) == 0u)) atomicOr(&s_ok[a], 1u << i);
+    }
+    __syncthreads();
+    const unsigned okx = s_ok[0], oky = s_ok[1], okz = s_ok[2];
+    const unsigned n_reg = (unsigned)(__popc(okx) * __popc(oky) * __popc(okz));
+    if (t == 0 && n_reg < (unsigned)P) s_exc_base = atomicAdd(p.exc_count, (unsigned)P - n_reg);
+    if (j >= 0 && n_reg) {
+      for (int l = 0; l < 3; l++) {
+        const double *C = p.vcoeff + (size_t)j * p.vstride + (size_t)l * p.ncoef_pad;
+        for (int e = t; e < (int)p.ncoef_pad; e += kTensorThreads) sC[e] = C[e];
+        __syncthreads();
+        // pass 1: rows (i,j) contracted with T_k(x) -- A[row][px]
+        for (int e = t; e < n_row * d; e += kTensorThreads) {
+          const int r = e / d, px = e - r * d;
+          // plane of the row: rows of plane i are row_first[i] .. row_first[i+1]-1, row length d-i-jj
+          int i = 0;
+          while (tb_.row_first[i + 1] <= r) i++;
+          const int len_r = d - i - (r - tb_.row_first[i]);
+          const double *c = sC + tb_.row_off[r], *T = sT + px;
+          double acc = 0.0;
+          for (int k = 0; k < len_r; k++) acc = fma(c[k], T[k * dp], acc);
+          sA[r * dp + px] = acc;
+        }
+        __syncthreads();
+        // pass 2: B[i][py][px] = sum_jj A[(i,jj)][px] T_jj(y_py)
+        for (int e = t; e < P; e += kTensorThreads) {
+          const int i = e / P2, rem = e - i * P2, py = rem / d, px = rem - py * d;
+          const double *A = sA + tb_.row_first[i] * dp + px, *T = sT + d * dp + py;
+          double acc = 0.0;
+          for (int jj = 0; jj < d - i; jj++) acc = fma(A[jj * dp], T[jj * dp], acc);
+          sB[e] = acc;
+        }
+        __syncthreads();
+        // pass 3: u[pz][py][px] = sum_i B[i][py][px] T_i(z_pz); x' = x + alpha * u on regular points
+        for (int e = t; e < P; e += kTensorThreads) {
+          const int pz = e / P2, rem = e - pz * P2, py = rem / d, px = rem - py * d;
+          if (!(((okx >> px) & (oky >> py) & (okz >> pz)) & 1u)) continue;
+          const double *B = sB + rem, *T = sT + 2 * d * dp + pz;
+          double acc = 0.0;
+          for (int i = 0; i < d; i++) acc = fma(B[i * P2], T[i * dp], acc);
+          const size_t o = 3 * (gp0 + e) + l;
+          p.out[o] = __dadd_rn(p.x[o], __dmul_rn(p.alpha, acc));  // traj.inc:36
+        }
+        __syncthreads();
+      }
+    }
+    if (n_reg < (unsigned)P) {  // list the exceptions of this leaf (CTA-uniform condition)
+      __syncthreads();          // s_exc_base is visible
+      for (int e = t; e < P; e += kTensorThreads) {
+        const int pz = e / P2, rem = e - pz * P2, py = rem / d, px = rem - py * d;
+        if (j >= 0 && (((okx >> px) & (oky >> py) & (okz >> pz)) & 1u)) continue;
+        const unsigned k = atomicAdd(&s_exc_n, 1u);
+        p.exc_idx[s_exc_base + k] = (uint32_t)(gp0 + e);
+      }
+    }
+  }
+}
+
+// The same for a compile-time degree (q <= 14): the three passes are register blocked so that the
+// FP64 pipe, not shared memory, bounds them.
+//   passes 1+2, thread = (plane i, px): T_k(x_px) in 15 registers; for every row j of the plane
+//     a_j = sum_k C[i][j][k] T_k(x_px) (coefficients: shared-memory reads shared by the px lanes),
+//     kept in registers; then B[i][py][px] = sum_j a_j T_j(y_py) for the 15 py (T_j(y_py) read as
+//     warp-wide broadcasts).  The intermediate A never touches shared memory.
+//   pass 3, thread = column (py,px): B[0..q][py][px] in 15 registers, u[pz] = sum_i B_i T_i(z_pz)
+//     for the 15 pz with broadcast reads of T_i(z_pz); epilogue x' = x + alpha u on regular points.
+template <int D>
+__global__ void __launch_bounds__(kTensorThreads)
+tensor_grid_eval_kernel_t(const TensorParams p, const TensorTables tb_) {
+  constexpr int DP = D | 1, DJ = (D + 1) & ~1, P2 = D * D, P = P2 * D, TOTAL = D * (D + 1) * (D + 2) / 6;
+  static_assert(P2 <= kTensorThreads, "one thread per (py,px) column");
+  extern __shared__ __align__(16) double sm[];
+  double *sT0 = sm;                  // [D][DP]  T_k(x_px), degree major
+  double *sT1 = sT0 + D * DP + (D * DP & 1);  // [D][DJ]  T_j(y_py), point major (rows 16-byte aligned)
+  double *sT2 = sT1 + D * DJ;        // [D][DJ]  T_i(z_pz), point major
+  double *sC3 = sT2 + D * DJ;        // [3][ncoef_pad] the velocity leaf's block, all components
+  double *sB = sC3 + p.vstride;      // [D][P2]
+  __shared__ unsigned s_ok[3];
+  __shared__ unsigned s_exc_base, s_exc_n;
+  const int t = threadIdx.x;
+  for (size_t leaf = blockIdx.x; leaf < p.n_leaf; leaf += gridDim.x) {
+    const int j = p.map[leaf];
+    const size_t gp0 = leaf * (size_t)P;
+    __syncthreads();
+    if (t < 3) s_ok[t] = 0u;
+    if (t == 0) s_exc_n = 0u;
+    if (j >= 0) {  // in flight while the bases are built
+      const double *C = p.vcoeff + (size_t)j * p.vstride;
+      for (int e = t; e < (int)p.vstride; e += kTensorThreads) sC3[e] = C[e];
+    }
+    __syncthreads();
+    if (j >= 0 && t < 3 * D) {
+      const int a = t / D, i = t - a * D;
+      const double4 gc = p.ggeom[leaf], gv = p.vgeom[j];
+      const uint4 vb = p.vbox[j];
+      const double len = 1.0 / (double)(1u << p.gdepth[leaf]);
+      const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z), vc = a == 0 ? gv.x : (a == 1 ? gv.y : gv.z);
+      const unsigned vba = a == 0 ? vb.x : (a == 1 ? vb.y : vb.z);
+      const double x = __dadd_rn(c, __dmul_rn(len, tb_.node[i]));            // gridpts.cu
+      const double xi = __dadd_rn(__dmul_rn(__dsub_rn(x, vc), gv.w), -1.0);  // cheb_eval.cuh
+      const bool in = fabs(xi) <= 1.0;
+      const double xc = in ? xi : 0.0, x2 = 2.0 * xc;
+      double t0 = in ? 1.0 : 0.0, t1 = xc;
+      // axis 0: [degree][point]; axes 1, 2: [point][degree]
+      double *T = a == 0 ? sT0 + i : (a == 1 ? sT1 : sT2) + i * DJ;
+      const int st = a == 0 ? DP : 1;
+      T[0] = t0;
+      if (D > 1) T[st] = t1;
+#pragma unroll
+      for (int k = 2; k < D; k++) {
+        const double t2 = __dsub_rn(__dmul_rn(x2, t1), t0);
+        T[k * st] = t2;
+        t0 = t1;
+        t1 = t2;
+      }
+      if (a != 0 && DJ > D) T[D] = 0.0;  // padding read by the paired loads
+      const double xs = x * 32768.0;
+      int jx = __double2int_rd(xs);
+      if (!p.periodic && xs == 32768.0) jx = 32767;
+      if ((unsigned)jx < 32768u && ((((unsigned)jx ^ vba) >> vb.w) == 0u)) atomicOr(&s_ok[a], 1u << i);
+    }
+    __syncthreads();
+    const unsigned okx = s_ok[0], oky = s_ok[1], okz = s_ok[2];
+    const unsigned n_reg = (unsigned)(__popc(okx) * __popc(oky) * __popc(okz));
+    if (t == 0 && n_reg < (unsigned)P) s_exc_base = atomicAdd(p.exc_count, (unsigned)P - n_reg);
+    if (j >= 0 && n_reg) {
+      const int pi = t / D, px = t - pi * D;      // passes 1+2: (plane, px)
+      const int py3 = t / D, px3 = t - py3 * D;   // pass 3: column (py, px) == t
+      double tx[D];
+      if (t < P2) {
+#pragma unroll
+        for (int k = 0; k < D; k++) tx[k] = sT0[k * DP + px];
+      }
+      // the grid point of (px3, py3, pz), recomputed as gridpts.cu forms it (bit-identical)
+      const double4 gc = p.ggeom[leaf];
+      const double glen = 1.0 / (double)(1u << p.gdepth[leaf]);
+      const double xq = __dadd_rn(gc.x, __dmul_rn(glen, tb_.node[px3 < D ? px3 : 0]));
+      const double yq = __dadd_rn(gc.y, __dmul_rn(glen, tb_.node[py3 < D ? py3 : 0]));
+      for (int l = 0; l < 3; l++) {
+        const double *sC = sC3 + l * p.ncoef_pad;
+        if (t < P2) {
+          const int m = D - pi;                                   // rows of plane pi
+          const int base = TOTAL - m * (m + 1) * (m + 2) / 6;     // its first coefficient
+          double a[D];
+#pragma unroll
+          for (int jj = 0; jj < D; jj++) {
+            const int len = m - jj;                               // <= 0: the row does not exist
+            const double *c = sC + base + jj * m - jj * (jj - 1) / 2;
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < D - jj; k++)
+              if (k < len) acc = fma(c[k], tx[k], acc);
+            a[jj] = acc;
+          }
+#pragma unroll 3
+          for (int py = 0; py < D; py++) {
+            const double *Ty = sT1 + py * DJ;
+            double acc = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < D; jj++) acc = fma(a[jj], Ty[jj], acc);  // a[jj] = 0 past the plane
+            sB[pi * P2 + py * D + px] = acc;
+          }
+        }
+        __syncthreads();
+        if (t < P2) {
+          double b[D];
+#pragma unroll
+          for (int i = 0; i < D; i++) b[i] = sB[i * P2 + t];
+          const bool col_ok = ((okx >> px3) & (oky >> py3)) & 1u;
+#pragma unroll 3
+          for (int pz = 0; pz < D; pz++) {
+            const double *Tz = sT2 + pz * DJ;
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) acc = fma(b[i], Tz[i], acc);
+            if (col_ok && ((okz >> pz) & 1u)) {
+              const size_t o = 3 * (gp0 + (size_t)pz * P2 + t) + l;
+              const double x0 = l == 0 ? xq : (l == 1 ? yq : __dadd_rn(gc.z, __dmul_rn(glen, tb_.node[pz])));
+              p.out[o] = __dadd_rn(x0, __dmul_rn(p.alpha, acc));  // traj.inc:36
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (n_reg < (unsigned)P) {  // list the exceptions of this leaf (CTA-uniform condition)
+      __syncthreads();
+      for (int e = t; e < P; e += kTensorThreads) {
+        const int pz = e / P2, rem = e - pz * P2, py = rem / D, px = rem - py * D;
+        if (j >= 0 && (((okx >> px) & (oky >> py) & (okz >> pz)) & 1u)) continue;
+        const unsigned k = atomicAdd(&s_exc_n, 1u);
+        p.exc_idx[s_exc_base + k] = (uint32_t)(gp0 + e);
+      }
+    }
+  }
+}
+
+template <int D>
+static int launch_tensor_t(tbslas_ctx *ctx, const TensorParams &p, const TensorTables &tt, size_t n_leaf) {
+  constexpr int DP = D | 1, DJ = (D + 1) & ~1;
+  const size_t smem = sizeof(double) * ((size_t)D * DP + (D * DP & 1) + 2 * D * DJ + p.vstride + (size_t)D * D * D);
+  auto k = tensor_grid_eval_kernel_t<D>;
+  TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  const size_t want = n_leaf < (size_t)ctx->n_sm * 16 ? n_leaf : (size_t)ctx->n_sm * 16;
+  k<<<(unsigned)want, kTensorThreads, smem, ctx->stream>>>(p, tt);
+  TB_CUDA(ctx, cudaGetLastError());
+  return TBSLAS_OK;
+}
+
+// exceptions: positions out, values back in
+__global__ void gather_points_kernel(const double *__restrict__ x, const uint32_t *__restrict__ idx, size_t m,
+                                     double *__restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * m) return;
+  const size_t s = e / 3;
+  out[e] = x[3 * (size_t)idx[s] + (e - 3 * s)];
+}
+__global__ void scatter_update_kernel(const double *__restrict__ pos, const double *__restrict__ val,
+                                      const uint32_t *__restrict__ idx, size_t m, double alpha, int periodic,
+                                      double *__restrict__ x, double *__restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * m) return;
+  const size_t s = e / 3, o = 3 * (size_t)idx[s] + (e - 3 * s);
+  const double b = pos[e];  // wrapped in place by the evaluation when periodic (tree_functor.h:442-449)
+  if (periodic) x[o] = b;
+  out[o] = __dadd_rn(b, __dmul_rn(alpha, val[e]));
+}
+
+// Stage 1 of the first RK2 sub-step on the grid points of leaves [leaf0, leaf0 + n_leaf) of `grid`:
+// out = x + alpha * vel(x).  `x` is rewritten only where the periodic wrap changes it.
+// Returns TBSLAS_ERR_UNSUPPORTED (without touching anything) when the shortcut does not apply.
+int eval_tree_dev_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out);  // api.cu
+
+int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree *grid, size_t leaf0,
+                            size_t n_leaf, int bc, double *x, double *out, double alpha) {
+  if (vel->dof != 3 || vel->q != grid->q || !vel->boxes_ok || !grid->boxes_ok || !vel->n_leaf ||
+      (ctx->nranks > 1 && !vel->replicated))
+    return TBSLAS_ERR_UNSUPPORTED;
+  const int d = vel->q + 1, dp = d | 1, P = d * d * d, n_row = d * (d + 1) / 2;
+  const size_t n = n_leaf * (size_t)P;
+  if (!n) return TBSLAS_OK;
+  if (n >= (size_t)0xfffffff0u) return TBSLAS_ERR_UNSUPPORTED;
+  TensorTables tt;
+  new_nodes_host(vel->q, tt.node);
+  int off = 0, r = 0;
+  for (int i = 0; i < d; i++) {
+    tt.row_first[i] = (uint16_t)r;
+    for (int j = 0; i + j < d; j++) {
+      tt.row_off[r++] = (uint16_t)off;
+      off += d - i - j;
+    }
+  }
+  tt.row_first[d] = (uint16_t)r;
+  void *map, *exc_idx, *misc;
+  TB_TRY(ws_get(ctx, WS_GRIDMAP, sizeof(int32_t) * n_leaf, &map));
+  TB_TRY(ws_get(ctx, WS_EXC_IDX, sizeof(uint32_t) * (n + 1), &exc_idx));
+  TB_TRY(ws_get(ctx, WS_MISC, 64, &misc));
+  unsigned *exc_count = (unsigned *)misc;
+  {
+    StageScope sc(ctx, ST_TENSOR, (double)n, 2);
+    TB_CUDA(ctx, cudaMemsetAsync(exc_count, 0, sizeof(unsigned), ctx->stream));
+    grid_leaf_map_kernel<<<(unsigned)((n_leaf + 255) / 256), 256, 0, ctx->stream>>>(
+        grid->d_box + leaf0, n_leaf, vel->d_key, vel->d_box, vel->d_cell, vel->cell_shift, (int)vel->n_leaf,
+        (int32_t *)map);
+    TB_CUDA(ctx, cudaGetLastError());
+    TensorParams p;
+    p.vcoeff = vel->d_coeff;
+    p.vgeom = vel->d_geom;
+    p.vbox = vel->d_box;
+    p.vstride = (unsigned)vel->stride;
+    p.ncoef_pad = (unsigned)(vel->stride / vel->dof);
+    p.ggeom = grid->d_geom + leaf0;
+    p.gdepth = grid->d_depth + leaf0;
+    p.map = (const int32_t *)map;
+    p.n_leaf = n_leaf;
+    p.d = d;
+    p.periodic = (bc == TBSLAS_PERIODIC);
+    p.x = x;
+    p.out = out;
+    p.alpha = alpha;
+    p.exc_count = exc_count;
+    p.exc_idx = (uint32_t *)exc_idx;
+    static const bool force_generic = getenv("TBSLAS_TENSOR_GENERIC") && atoi(getenv("TBSLAS_TENSOR_GENERIC"));
+    switch (force_generic ? 0 : d) {
+#define TB_CASE(DD) \
+  case DD:          \
+    TB_TRY(launch_tensor_t<DD>(ctx, p, tt, n_leaf)); \
+    break;
+      TB_CASE(2) TB_CASE(3) TB_CASE(4) TB_CASE(5) TB_CASE(6) TB_CASE(7) TB_CASE(8) TB_CASE(9)
+      TB_CASE(10) TB_CASE(11) TB_CASE(12) TB_CASE(13) TB_CASE(14) TB_CASE(15)
+#undef TB_CASE
+      default: {  // degree-generic kernel (q = 15..19)
+        const size_t smem = sizeof(double) * ((size_t)3 * d * dp + p.ncoef_pad + (size_t)n_row * dp + (size_t)d * d * d);
+        TB_CUDA(ctx, cudaFuncSetAttribute(tensor_grid_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t want = n_leaf < (size_t)ctx->n_sm * 16 ? n_leaf : (size_t)ctx->n_sm * 16;
+        tensor_grid_eval_kernel<<<(unsigned)want, kTensorThreads, smem, ctx->stream>>>(p, tt);
+        TB_CUDA(ctx, cudaGetLastError());
+      }
+    }
+  }
+  // the exceptions go through the generic path: one host-visible count per call
+  TB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, exc_count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const size_t m = ctx->h_counts[0];
+  ctx->last_exceptions = m;
+  if (!m) return TBSLAS_OK;
+  void *epos, *eval;
+  // sized with headroom: the count differs a little from call to call and a growing workspace
+  // slot is a cudaFree + cudaMalloc
+  const size_t cap = m > n / 8 + 4096 ? m + m / 4 : n / 8 + 4096;
+  TB_TRY(ws_get(ctx, WS_EXC_POS, sizeof(double) * 3 * cap, &epos));
+  TB_TRY(ws_get(ctx, WS_EXC_VAL, sizeof(double) * 3 * cap, &eval));
+  const unsigned g3 = (unsigned)((3 * m + 255) / 256);
+  {
+    StageScope sc(ctx, ST_TENSOR, 0.0, 1);
+    gather_points_kernel<<<g3, 256, 0, ctx->stream>>>(x, (const uint32_t *)exc_idx, m, (double *)epos);
+    TB_CUDA(ctx, cudaGetLastError());
+  }
+  TB_TRY(eval_tree_dev_points(vel, bc, (double *)epos, m, (double *)eval));
+  {
+    StageScope sc(ctx, ST_TENSOR, 0.0, 1);
+    scatter_update_kernel<<<g3, 256, 0, ctx->stream>>>((const double *)epos, (const double *)eval,
+                                                       (const uint32_t *)exc_idx, m, alpha,
+                                                       bc == TBSLAS_PERIODIC, x, out);
+    TB_CUDA(ctx, cudaGetLastError());
+  }
+  return TBSLAS_OK;
+}
+
+}  // namespace tb

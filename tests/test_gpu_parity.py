@@ -341,8 +341,52 @@ def test_gpu_semilag_insitu_equals_explicit_points(ctx):
     pts = tcon.collect_grid_points()
     for bc in (0, 1):
         a = api.SolveSemilagRK2(vel, con, pts, 2, 0.04, 2, bc)
+        ctx.set_tensor_grid(False)   # every evaluation point by point: the very same arithmetic
         b = api.SolveSemilagInSitu(vel, tcon, 2, 0.04, 2, bc)
+        ctx.set_tensor_grid(True)    # first velocity evaluation by sum factorisation (default)
+        c = api.SolveSemilagInSitu(vel, tcon, 2, 0.04, 2, bc)
         assert np.array_equal(a, b)
+        assert rel_err(c, a) < 1e-11
+
+
+@pytest.mark.parametrize("case", ["same_tree", "velocity_coarser", "velocity_finer", "time_varying"])
+@pytest.mark.parametrize("bc", [0, 1])
+def test_gpu_tensor_grid_velocity_vs_generic_and_oracle(ctx, port, case, bc):
+    """tensor_eval.cu: the velocity at the arrival grids by sum factorisation against the
+    point-by-point path (same library, switch off) and against the oracle's step, for advected
+    leaves equal to, finer than and COARSER than the velocity leaves (the last: no containing
+    velocity leaf, every point takes the generic path), both boundary conditions (grid points on
+    leaf faces and on the domain boundary are the exceptions), and a 4-snapshot velocity."""
+    api = _api()
+    q = 5
+    coord, dd = adaptive_leaves(4, 2)
+    if case == "same_tree":
+        vc, vd = coord, dd
+    elif case == "velocity_coarser":
+        vc, vd = ftm.uniform_leaves(1)
+    else:
+        vc, vd = ftm.uniform_leaves(3) if case == "velocity_finer" else ftm.uniform_leaves(2)
+    fcon = ftm.fit(coord, dd, q, 1, lambda p: ftm.gaussian(p, (0.5, 0.5, 0.5), 0.25))
+    tcon = ctx.tree(fcon)
+    if case == "time_varying":
+        times = [-0.05, 0.0, 0.05, 0.1]
+        fv = [ftm.fit(vc, vd, q, 3, lambda p, s=s: ftm.vel_rotation(p) * s) for s in (0.8, 1.0, 1.2, 0.9)]
+        vel = api.FieldSetFunctor([ctx.tree(f) for f in fv], times)
+    else:
+        # a velocity that is DIScontinuous across leaves (random coefficients): a grid point on a leaf
+        # face evaluated by the wrong leaf would be off by O(0.1)
+        fvel = ftm.random_tree(vc, vd, q, 3, seed=41, scale=0.2)
+        vel = api.NodeFieldFunctor(ctx.tree(fvel))
+    ctx.set_tensor_grid(False)
+    ref = api.SolveSemilagInSitu(vel, tcon, 1, 0.05, 1, bc)
+    ctx.set_tensor_grid(True)
+    got = api.SolveSemilagInSitu(vel, tcon, 1, 0.05, 1, bc)
+    assert rel_err(got, ref) < 1e-11
+    if case != "time_varying":
+        hv, hc = port.tree_create(fvel), port.tree_create(fcon)
+        pts = ftm.grid_points(coord, dd, q)
+        want = port.semilag_rk2(hv, hc, 1, pts, 1, 0.05, 1, bc)
+        assert rel_err(got, want) < 1e-11
 
 
 @pytest.mark.parametrize("q,dof,n_leaf", [(4, 1, 8), (8, 3, 300), (14, 1, 137), (14, 3, 64), (5, 2, 1)])
