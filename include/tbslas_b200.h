@@ -175,8 +175,9 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2,
  * sum factorisation (three 1-D passes per leaf: 88 k instead of 2.75 M FMA per leaf and component
  * at q = 14) -- the same polynomial at the same points summed in another order, ~1e-15 of the field
  * scale; grid points on a velocity-leaf face, and leaves not inside one velocity leaf, take the
- * generic path, so every point is evaluated by the leaf the reference assigns it to.  mode 0:
- * every evaluation is point by point. */
+ * generic path, so every point is evaluated by the leaf the reference assigns it to.  Calls on
+ * fewer than 4 Mi points keep the generic path (latency bound either way); mode 2 removes that
+ * minimum (tests).  mode 0: every evaluation is point by point. */
 int tbslas_b200_set_tensor_grid(tbslas_ctx *ctx, int mode);
 /* Arrival points of the most recent tree-level call (or of its last chunk, for host buffers) that
  * took the generic path instead (on a velocity-leaf face, or in a leaf not inside one velocity leaf). */

@@ -92,7 +92,7 @@ class Context:
     def set_tensor_grid(self, on: bool) -> None:
         """Tree-level calls: evaluate the velocity at the arrival grids by sum factorisation
         (True, default) or point by point (False)."""
-        self.check(self.lib.tbslas_b200_set_tensor_grid(self.h, int(bool(on))))
+        self.check(self.lib.tbslas_b200_set_tensor_grid(self.h, 2 if on == "always" else int(bool(on))))
 
     def last_grid_exceptions(self) -> int:
         n = C.c_size_t()

@@ -346,7 +346,8 @@ static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, 
     double *x = (s == 0 && x0) ? const_cast<double *>(x0) : xsol;  // not written unless periodic
     // v1 = V(x, t);  xtmp = x + 0.5*tau*v1      traj.inc:33-36 (x wrapped in place if periodic)
     bool done = false;
-    if (s == 0 && grid && ctx->tensor_grid && x == xsol && n) {
+    // (small point sets are latency bound either way and the shortcut costs a host-visible count)
+    if (s == 0 && grid && ctx->tensor_grid && x == xsol && n >= ctx->tensor_grid_min_points) {
       const size_t P = (size_t)(grid->q + 1) * (grid->q + 1) * (grid->q + 1);
       tbslas_tree view, *one = nullptr;
       TB_TRY(field_single_tree(ctx, f1, tcur, &view, &one));
@@ -593,8 +594,9 @@ int tbslas_b200_last_grid_exceptions(tbslas_ctx *ctx, size_t *n) {
 }
 
 int tbslas_b200_set_tensor_grid(tbslas_ctx *ctx, int mode) {
-  if (!ctx || (mode != 0 && mode != 1)) return TBSLAS_ERR_INVALID;
-  ctx->tensor_grid = mode;
+  if (!ctx || mode < 0 || mode > 2) return TBSLAS_ERR_INVALID;
+  ctx->tensor_grid = mode != 0;
+  ctx->tensor_grid_min_points = mode == 2 ? 1 : (size_t)4 << 20;
   return TBSLAS_OK;
 }
 

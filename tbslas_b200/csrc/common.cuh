@@ -119,6 +119,7 @@ struct tbslas_ctx {
   // tree-level calls (semilag_insitu*): 1 = the velocity at the arrival grids is evaluated by sum
   // factorisation (tensor_eval.cu), 0 = point by point like any other point set
   int tensor_grid = 1;
+  size_t tensor_grid_min_points = (size_t)4 << 20;  // tbslas_b200_set_tensor_grid(ctx, 2): no minimum
   size_t last_exceptions = 0;  // arrival points of the last such call that took the generic path
   // pinned host scratch for small device->host reads (exchange counts: [nranks][nranks])
   unsigned *h_counts = nullptr;

@@ -36,16 +36,22 @@ grid_points_kernel(const double4 *__restrict__ geom, const uint8_t *__restrict__
   __shared__ double s_node[TBSLAS_MAX_CHEB_DEG + 1];
   if (threadIdx.x <= TBSLAS_MAX_CHEB_DEG) s_node[threadIdx.x] = nodes.x[threadIdx.x];
   __syncthreads();
-  const unsigned ud = (unsigned)d, dd = ud * ud, P3 = 3u * dd * ud;
+  const unsigned ud = (unsigned)d, dd = ud * ud, row_len = 3u * ud;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warp = blockDim.x >> 5;
   for (size_t leaf = blockIdx.x; leaf < n_leaf; leaf += gridDim.x) {
     const double4 g = geom[leaf];
     const double len = 1.0 / (double)(1u << depth[leaf]);  // pow(0.5, depth), exact
-    double *o = out + leaf * P3;
-    for (unsigned r = threadIdx.x; r < P3; r += blockDim.x) {
-      const unsigned pt = r / 3u, a = r - 3u * pt;
-      const unsigned ix = (a == 0) ? pt % ud : (a == 1) ? (pt / ud) % ud : pt / dd;
-      const double c = (a == 0) ? g.x : (a == 1) ? g.y : g.z;
-      o[r] = __dadd_rn(c, __dmul_rn(len, s_node[ix]));
+    double *o = out + leaf * (size_t)(3u * dd * ud);
+    // a warp writes one x-row of the grid (3*d contiguous doubles) per iteration
+    for (unsigned row = warp; row < dd; row += n_warp) {
+      const unsigned iz = row / ud, iy = row - iz * ud;
+      const double y = __dadd_rn(g.y, __dmul_rn(len, s_node[iy]));
+      const double z = __dadd_rn(g.z, __dmul_rn(len, s_node[iz]));
+      double *orow = o + (size_t)row * row_len;
+      for (unsigned e = lane; e < row_len; e += 32) {
+        const unsigned ix = e / 3u, a = e - 3u * ix;
+        orow[e] = (a == 0) ? __dadd_rn(g.x, __dmul_rn(len, s_node[ix])) : (a == 1 ? y : z);
+      }
     }
   }
 }

@@ -122,6 +122,19 @@ def main():
     same("replicated velocity: semilag",
          api.SolveSemilagRK2(rvel, api.NodeFieldFunctor(tcon), arr, 3, 0.05, 2, 1),
          api.SolveSemilagRK2(api.NodeFieldFunctor(svel[1]), api.NodeFieldFunctor(scon), arr, 3, 0.05, 2, 1))
+    # (4c) the tree-level step: arrival points generated on the device from this rank's leaves, the
+    # first velocity evaluation by sum factorisation over those grids (replicated velocity tree),
+    # the scalar through the exchange -- against the single-rank context's tree-level step on the
+    # whole tree, restricted to this rank's leaves
+    P = (q + 1) ** 3
+    lo, hi = int(first[rank]) * P, int(first[rank + 1]) * P
+    rtree = ctx.tree(vels[1], replicated=True)
+    ctx.set_tensor_grid("always")
+    solo.set_tensor_grid("always")
+    for bc in (0, 1):
+        a = api.SolveSemilagInSitu(api.NodeFieldFunctor(rtree), tcon, 2, 0.05, 1, bc)
+        b = api.SolveSemilagInSitu(api.NodeFieldFunctor(svel[1]), scon, 2, 0.05, 1, bc)
+        same("tree-level step (tensor grids) bc%d" % bc, a, b[lo:hi])
     # (5) empty point set on one rank (the call is still collective)
     e = pts[:0].copy() if rank == world - 1 else pts[:777].copy()
     same("ragged: empty input on the last rank", api.NodeFieldFunctor(tcon)(e.copy(), bc=0),

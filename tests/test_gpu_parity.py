@@ -343,10 +343,11 @@ def test_gpu_semilag_insitu_equals_explicit_points(ctx):
         a = api.SolveSemilagRK2(vel, con, pts, 2, 0.04, 2, bc)
         ctx.set_tensor_grid(False)   # every evaluation point by point: the very same arithmetic
         b = api.SolveSemilagInSitu(vel, tcon, 2, 0.04, 2, bc)
-        ctx.set_tensor_grid(True)    # first velocity evaluation by sum factorisation (default)
+        ctx.set_tensor_grid("always")  # first velocity evaluation by sum factorisation (any size)
         c = api.SolveSemilagInSitu(vel, tcon, 2, 0.04, 2, bc)
         assert np.array_equal(a, b)
         assert rel_err(c, a) < 1e-11
+    ctx.set_tensor_grid(True)
 
 
 @pytest.mark.parametrize("case", ["same_tree", "velocity_coarser", "velocity_finer", "time_varying"])
@@ -379,8 +380,10 @@ def test_gpu_tensor_grid_velocity_vs_generic_and_oracle(ctx, port, case, bc):
         vel = api.NodeFieldFunctor(ctx.tree(fvel))
     ctx.set_tensor_grid(False)
     ref = api.SolveSemilagInSitu(vel, tcon, 1, 0.05, 1, bc)
-    ctx.set_tensor_grid(True)
+    ctx.set_tensor_grid("always")
     got = api.SolveSemilagInSitu(vel, tcon, 1, 0.05, 1, bc)
+    assert ctx.last_grid_exceptions() > 0
+    ctx.set_tensor_grid(True)
     assert rel_err(got, ref) < 1e-11
     if case != "time_varying":
         hv, hc = port.tree_create(fvel), port.tree_create(fcon)
