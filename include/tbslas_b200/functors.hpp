@@ -84,6 +84,11 @@ class Context {
   void check(int rc) const {
     if (rc != TBSLAS_OK) throw Error(rc, std::string("tbslas_b200: ") + tbslas_b200_last_error(p_.get()));
   }
+  // Evaluation shortcuts (both on by default): coefficients of snapshot trees
+  // with one leaf list combined in time before a single evaluation, and the first velocity
+  // evaluation of a tree-level step by sum factorisation over the arrival grids.
+  void SetTimeCombine(bool on) { check(tbslas_b200_set_time_combine(p_.get(), on ? 1 : 0)); }
+  void SetTensorGrid(bool on) { check(tbslas_b200_set_tensor_grid(p_.get(), on ? 1 : 0)); }
   // Multi-GPU: `bcast128(void* buf)` must broadcast 128 bytes from rank 0 to all ranks
   // (MPI_Bcast(buf,128,MPI_BYTE,0,comm) in an MPI host such as the reference's drivers).
   template <class Bcast128>
