@@ -29,6 +29,9 @@
 namespace tb {
 
 constexpr int kTensorThreads = 256;
+#ifndef TB_TENSOR_MINB
+#define TB_TENSOR_MINB 2
+#endif
 constexpr int kMaxD = TBSLAS_MAX_CHEB_DEG + 1;
 constexpr int kMaxRows = kMaxD * (kMaxD + 1) / 2;
 
@@ -192,7 +195,7 @@ tensor_grid_eval_kernel(const TensorParams p, const TensorTables tb_) {
 //   pass 3, thread = column (py,px): B[0..q][py][px] in 15 registers, u[pz] = sum_i B_i T_i(z_pz)
 //     for the 15 pz with broadcast reads of T_i(z_pz); epilogue x' = x + alpha u on regular points.
 template <int D>
-__global__ void __launch_bounds__(kTensorThreads)
+__global__ void __launch_bounds__(kTensorThreads, TB_TENSOR_MINB)
 tensor_grid_eval_kernel_t(const TensorParams p, const TensorTables tb_) {
   constexpr int DP = D | 1, DJ = (D + 1) & ~1, P2 = D * D, P = P2 * D, TOTAL = D * (D + 1) * (D + 2) / 6;
   static_assert(P2 <= kTensorThreads, "one thread per (py,px) column");
