@@ -742,13 +742,15 @@ int tbslas_b200_tree_update_coeff(tbslas_tree *t, const double *coeff, int mem) 
   tbslas_ctx *ctx = t->ctx;
   const size_t ncoef_pad = t->stride / t->dof;
   StageScope sc(ctx, ST_H2D, (double)(t->n_leaf * t->dof * t->ncoef * 8), 0);
-  // [leaf][dof][Ncoef] -> rows padded to an even number of doubles
-  TB_CUDA(ctx, cudaMemcpy2DAsync(t->d_coeff, ncoef_pad * sizeof(double), coeff,
-                                 t->ncoef * sizeof(double), t->ncoef * sizeof(double),
-                                 t->n_leaf * t->dof,
-                                 mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice
-                                                          : cudaMemcpyHostToDevice,
+  // [leaf][dof][Ncoef] -> rows padded to an even number of doubles (one flat copy when Ncoef is
+  // even already: a pitched copy is one DMA descriptor per 5 KB row)
+  const cudaMemcpyKind kind = mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (ncoef_pad == t->ncoef)
+    TB_CUDA(ctx, cudaMemcpyAsync(t->d_coeff, coeff, sizeof(double) * t->ncoef * t->n_leaf * t->dof, kind,
                                  ctx->stream));
+  else
+    TB_CUDA(ctx, cudaMemcpy2DAsync(t->d_coeff, ncoef_pad * sizeof(double), coeff, t->ncoef * sizeof(double),
+                                   t->ncoef * sizeof(double), t->n_leaf * t->dof, kind, ctx->stream));
   if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TBSLAS_OK;
 }
@@ -759,10 +761,13 @@ int tbslas_b200_tree_get_coeff(tbslas_tree *t, double *coeff, int mem) {
   if (!t->n_leaf) return TBSLAS_OK;
   const size_t ncoef_pad = t->stride / t->dof;
   StageScope sc(ctx, ST_D2H, (double)(t->n_leaf * t->dof * t->ncoef * 8), 0);
-  TB_CUDA(ctx, cudaMemcpy2DAsync(coeff, t->ncoef * sizeof(double), t->d_coeff, ncoef_pad * sizeof(double),
-                                 t->ncoef * sizeof(double), t->n_leaf * t->dof,
-                                 mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+  const cudaMemcpyKind kind = mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (ncoef_pad == t->ncoef)
+    TB_CUDA(ctx, cudaMemcpyAsync(coeff, t->d_coeff, sizeof(double) * t->ncoef * t->n_leaf * t->dof, kind,
                                  ctx->stream));
+  else
+    TB_CUDA(ctx, cudaMemcpy2DAsync(coeff, t->ncoef * sizeof(double), t->d_coeff, ncoef_pad * sizeof(double),
+                                   t->ncoef * sizeof(double), t->n_leaf * t->dof, kind, ctx->stream));
   if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TBSLAS_OK;
 }
