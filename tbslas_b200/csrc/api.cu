@@ -544,7 +544,7 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
   cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
   for (auto &pair : ctx->ev_pipe)
     for (cudaEvent_t &e : pair) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-  cudaMallocHost(&ctx->h_counts, sizeof(unsigned) * kMaxRanks * kMaxRanks);
+  cudaHostAlloc(&ctx->h_counts, sizeof(unsigned) * kMaxRanks * kMaxRanks, cudaHostAllocMapped | cudaHostAllocPortable);  // device-writable (tensor_eval.cu)
   *out = ctx;
   return TBSLAS_OK;
 }

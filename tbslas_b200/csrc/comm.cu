@@ -179,6 +179,11 @@ __global__ void unpack_kernel(const double *__restrict__ val, const int32_t *__r
 
 int eval_received_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out, int32_t *leaf_out);
 
+__global__ void publish_words_kernel(const uint32_t *__restrict__ src, unsigned *host_dst, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) reinterpret_cast<volatile unsigned *>(host_dst)[i] = src[i];
+  __threadfence_system();
+}
+
 // Step 1 (right after locate): the nranks x nranks matrix of send counts, to pinned host
 // memory; runs on the comm stream so the caller keeps enqueueing insider work.
 int comm_begin_exchange(tbslas_ctx *ctx, const uint32_t *send_count_dev) {
@@ -188,8 +193,10 @@ int comm_begin_exchange(tbslas_ctx *ctx, const uint32_t *send_count_dev) {
   StageScope sc(ctx, ST_EXCHANGE, 0.0, 0);
   TB_TRY(chain(ctx, ctx->stream, ctx->comm_stream));
   TB_NCCL(ctx, g_nccl.AllGather(send_count_dev, buf, np, ncclUint32, comm_of(ctx), ctx->comm_stream));
-  TB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, buf, sizeof(uint32_t) * np * np, cudaMemcpyDeviceToHost,
-                               ctx->comm_stream));
+  // stored by a kernel into the device-accessible pinned matrix: a cudaMemcpy would queue on the
+  // device-to-host copy engine behind whatever bulk copy-out is in flight (pipelined host calls)
+  publish_words_kernel<<<1, 256, 0, ctx->comm_stream>>>((const uint32_t *)buf, ctx->h_counts, np * np);
+  TB_CUDA(ctx, cudaGetLastError());
   TB_CUDA(ctx, cudaEventRecord(ctx->ev_counts, ctx->comm_stream));
   return TBSLAS_OK;
 }

@@ -338,6 +338,11 @@ static int launch_tensor_t(tbslas_ctx *ctx, const TensorParams &p, const TensorT
   return TBSLAS_OK;
 }
 
+__global__ void publish_count_kernel(const unsigned *__restrict__ src, unsigned *host_word) {
+  *reinterpret_cast<volatile unsigned *>(host_word) = *src;
+  __threadfence_system();
+}
+
 // exceptions: positions out, values back in
 __global__ void gather_points_kernel(const double *__restrict__ x, const uint32_t *__restrict__ idx, size_t m,
                                      double *__restrict__ out) {
@@ -429,8 +434,12 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
       }
     }
   }
-  // the exceptions go through the generic path: one host-visible count per call
-  TB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, exc_count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  // The exceptions go through the generic path: one host-visible count per call.  A kernel stores it
+  // into the (device-accessible) pinned word: a cudaMemcpy would queue on the device-to-host copy
+  // engine behind the previous chunk's values (hundreds of MB in the pipelined host calls) and stall
+  // this stream for as long as that copy takes.
+  publish_count_kernel<<<1, 1, 0, ctx->stream>>>(exc_count, ctx->h_counts);
+  TB_CUDA(ctx, cudaGetLastError());
   TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   const size_t m = ctx->h_counts[0];
   ctx->last_exceptions = m;
