@@ -149,6 +149,9 @@ int tbslas_b200_eval_extrap(tbslas_tree *tp, tbslas_tree *tc, int bc, double *po
  * combined per point exactly as tree_set_functor.h:55-72 / tree_extrap_functor.h:59-77 do.
  * Trees with different leaf lists always take the mode-0 route. */
 int tbslas_b200_set_time_combine(tbslas_ctx *ctx, int mode);
+/* The weights of that combination, host only: InterpCubic1D (cubic.h:36-56) is linear in the four
+ * snapshot values, out = w[0] p0 + w[1] p1 + w[2] p2 + w[3] p3. */
+int tbslas_b200_cubic_time_weights(const double times[4], double t, double w[4]);
 /* Any field kind through one entry point (t is ignored by STEADY and EXTRAP). */
 int tbslas_b200_eval_field(const tbslas_field *f, double t, int bc, double *pos, size_t n,
                            double *out, int mem);

@@ -21,7 +21,7 @@ MAX_CHEB_DEG = 19
 # every symbol include/tbslas_b200.h declares (tests check the export table against it)
 SYMBOLS = [
     "tbslas_b200_init", "tbslas_b200_finalize", "tbslas_b200_set_stream",
-    "tbslas_b200_synchronize", "tbslas_b200_set_time_combine", "tbslas_b200_set_tensor_grid", "tbslas_b200_last_grid_exceptions", "tbslas_b200_last_error", "tbslas_b200_version",
+    "tbslas_b200_synchronize", "tbslas_b200_set_time_combine", "tbslas_b200_cubic_time_weights", "tbslas_b200_set_tensor_grid", "tbslas_b200_last_grid_exceptions", "tbslas_b200_last_error", "tbslas_b200_version",
     "tbslas_b200_comm_unique_id", "tbslas_b200_comm_init", "tbslas_b200_comm_rank",
     "tbslas_b200_comm_last_exchange",
     "tbslas_b200_tree_create", "tbslas_b200_tree_create_replicated", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_get_coeff", "tbslas_b200_tree_destroy",
@@ -66,6 +66,7 @@ def load() -> C.CDLL:
     L.tbslas_b200_set_stream.argtypes = [vp, vp]
     L.tbslas_b200_synchronize.argtypes = [vp]
     L.tbslas_b200_set_time_combine.argtypes = [vp, C.c_int]
+    L.tbslas_b200_cubic_time_weights.argtypes = [C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
     L.tbslas_b200_set_tensor_grid.argtypes = [vp, C.c_int]
     L.tbslas_b200_last_grid_exceptions.argtypes = [vp, C.POINTER(sz)]
     L.tbslas_b200_last_error.argtypes = [vp]

@@ -1048,6 +1048,12 @@ int tbslas_b200_owner_of_key(uint64_t key, const uint64_t *splitters, int nranks
   return owner;
 }
 
+int tbslas_b200_cubic_time_weights(const double times[4], double t, double w[4]) {
+  if (!times || !w) return TBSLAS_ERR_INVALID;
+  cubic_time_weights(times, t, w);
+  return TBSLAS_OK;
+}
+
 int tbslas_b200_partition_leaves(size_t n_leaf, int nranks, size_t *first) {
   if (nranks < 1 || !first) return TBSLAS_ERR_INVALID;
   for (int r = 0; r <= nranks; r++) first[r] = (size_t)r * n_leaf / nranks;

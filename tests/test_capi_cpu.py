@@ -88,6 +88,26 @@ def test_weighted_partition():
         partition_leaves_weighted(np.array([1.0, -1.0]), 2)
 
 
+def test_cubic_time_weights_reproduce_interp_cubic1d(port):
+    """The weights behind the one-evaluation route of FieldSetFunctor: sum_k w_k p_k must equal the
+    reference's InterpCubic1D (cubic.h:36-56, restated in the oracle) for any snapshot values,
+    uniform and non-uniform snapshot times, query times inside and outside [t1, t2]."""
+    lib = capi.load()
+    rng = np.random.default_rng(11)
+    for times in ([-0.05, 0.0, 0.05, 0.1], [0.0, 0.3, 0.35, 1.0], [1.0, 2.0, 4.0, 4.5]):
+        tt = (C.c_double * 4)(*times)
+        for tq in (times[1], times[2], 0.5 * (times[1] + times[2]), times[1] + 0.123 * (times[2] - times[1]),
+                   times[2] + 0.2 * (times[2] - times[1])):
+            w = (C.c_double * 4)()
+            assert lib.tbslas_b200_cubic_time_weights(tt, tq, w) == 0
+            w = np.array(w[:])
+            assert abs(w.sum() - 1.0) < 1e-13          # constants are reproduced
+            for _ in range(20):
+                p = rng.standard_normal(4)
+                want = port.interp_cubic1d(tq, np.array(times), p)
+                assert abs(w @ p - want) <= 1e-13 * (1 + np.abs(p).max() * np.abs(w).max())
+
+
 def test_new_nodes_matches_oracle(port):
     from tbslas_b200.api import new_nodes
     for q in range(1, 17):
