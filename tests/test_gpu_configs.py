@@ -188,3 +188,30 @@ def test_config5_uniform_depth5_full_size(ctx):
         ctx.set_stream(None)
         tcon.destroy()
         tz.destroy()
+
+
+def test_bench_line_contract_on_a_reduced_workload():
+    """bench.py (B200 arm) on a shrunken C2: ONE JSON line with the keys the driver reads, the
+    roofline and CPU-baseline objects, a non-zero launch count and consistent checksums between the
+    two end-to-end flavours."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--scale", "2", "--steps", "2",
+                        "--cpu-leaves", "64"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "e2e", "roofline",
+              "cpu_baseline"):
+        assert k in d, k
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["warmup"] >= 3 and d["dtype"] == "f64"
+    assert d["roofline"]["frac"] > 0 and d["roofline"]["peak"] > 0 and d["roofline"]["unit"] == "TFLOP/s"
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert abs(e["checksum"] - e["point_array_call"]["checksum"]) <= 1e-9 * max(1.0, abs(e["checksum"]))
