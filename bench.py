@@ -137,6 +137,14 @@ class ClockSampler:
                 "samples": len(sm), "window": window}
 
 
+def workload_config(wl, world=1):
+    """The keys both arms print (the driver compares them): what the workload IS, not how an arm runs
+    it; plus `sample` (None on the B200 arm, which runs all of it)."""
+    return {"workload": "%s: %s" % (wl.name, wl.desc), "leaves": wl.con.n_leaf, "points_total": wl.n_points,
+            "q": wl.q, "bc": "periodic" if wl.bc else "freespace", "dt": wl.dt, "nrk": 1,
+            "velocity_trees": len(wl.vel), "velocity_leaves": wl.vel[0].n_leaf}
+
+
 # --------------------------------------------------------------------------- reference arm
 def sample_points(wl, n_leaves, seed=0):
     """Arrival points of an evenly strided subset of the advected tree's leaves."""
@@ -166,8 +174,8 @@ def cpu_run(wl, pts, steps, warmup, threads=None):
             orc.semilag_rk2(hv, hc, 1, pts, 1, wl.dt, 1, wl.bc, kind="set4", times=wl.vel_times)
         if it >= warmup:
             ts.append(time.perf_counter() - t0)
-    best = float(np.mean(ts))
-    return pts.shape[0] / best, kind, cores, best
+    mean = float(np.mean(ts))
+    return pts.shape[0] / mean, kind, cores, mean
 
 
 def run_reference(args):
@@ -185,8 +193,11 @@ def run_reference(args):
         "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (wl.name, wl.desc), "points_total": wl.n_points,
-                   "sample": "%d of %d leaves (%d points) per step" % (nl, wl.con.n_leaf, pts.shape[0])},
+        "config": dict(workload_config(wl),
+                       sample={"leaves": nl, "points_per_step": int(pts.shape[0]),
+                               "what": "each step = SolveSemilagRK2 over the arrival points of %d evenly "
+                                       "strided leaves of the %d (full trees): the whole workload would take "
+                                       "~%.0f s per step on these cores" % (nl, wl.con.n_leaf, wl.n_points / rate)}),
         "cpu_baseline": {"value": rate, "unit": "points/s", "cores": cores, "kind": kind,
                          "sample": "SolveSemilagRK2 on the arrival points of %d evenly strided leaves "
                                    "(%d points), full trees; single-rank OpenMP path over a PVFMM "
@@ -258,6 +269,8 @@ def run_b200(args):
     ctx.set_stream(torch.cuda.current_stream())
     if world > 1:
         ctx.comm_init_torch()
+        if args.exchange:
+            ctx.comm_set_exchange(args.exchange)
         # the advected tree in equal-count contiguous Morton ranges; the velocity tree
         # re-partitioned with the SAME break points, whole leaves by their own Morton id
         # (what tbslas::MergeTree + RedistNodes do, tree_utils.h:703-728)
@@ -345,6 +358,59 @@ def run_b200(args):
     value = n_total / (ms_per_step * 1e-3)
     m_exc = ctx.last_grid_exceptions()
 
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def checksums(v):
+        """(float sum, sum of the values' BIT PATTERNS mod 2^64) over all ranks.  Integer addition
+        wraps and commutes, so the second is independent of the partition and of summation order:
+        bit-identical values give the same number at N = 1, 2, 4, 8."""
+        f = v.sum().reshape(1).to(dev)
+        b = v.contiguous().view(torch.int64).sum().reshape(1).to(dev)
+        if world > 1:
+            dist.all_reduce(f, op=dist.ReduceOp.SUM)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        return float(f.item()), int(b.item())
+    checksum_dev, checksum_bits = checksums(vals)
+
+    # ---- parity of the timed path against the oracle, outside the timed region ------------
+    # A strided sample of THIS rank's arrival points through the oracle (CPU restatement of the
+    # reference, full trees): departure points, values at the GPU's departure points, composed step.
+    parity = None
+    if not args.no_parity:
+        from oracle import Oracle
+        orc = Oracle("port")
+        pv, pdep = api.SolveSemilagInSitu(vel_f, tcon, 1, wl.dt, 1, wl.bc, device=True, departure_points=True)
+        torch.cuda.synchronize()
+        same_bits = bool(torch.equal(pv, vals))
+        n_s = min(args.parity_points, n_local)
+        e_dep = e_val = e_step = 0.0
+        if n_s:
+            idx = torch.linspace(0, n_local - 1, n_s, device=dev).long()
+            arr, dep_g, got = pos[idx].cpu().numpy(), pdep[idx].cpu().numpy(), pv[idx].cpu().numpy()
+            hv = [orc.tree_create(v) for v in wl.vel]
+            hc = orc.tree_create(wl.con)
+            kind, vh = ("steady", hv[0]) if len(hv) == 1 else ("set4", hv)
+            dep_o = orc.traj_rk2(vh, arr, wl.dt, 0.0, 1, wl.bc, kind=kind, times=wl.vel_times)
+            want_g, _, _ = orc.eval_tree(hc, 1, dep_g, wl.bc, want_leaf=False)
+            want = orc.semilag_rk2(vh, hc, 1, arr, 1, wl.dt, 1, wl.bc, kind=kind, times=wl.vel_times)
+            sc = max(float(np.abs(want).max()), 1e-300)
+            e_dep = float(np.abs(dep_g - dep_o).max())
+            e_val = float(np.abs(got - want_g).max()) / sc
+            e_step = float(np.abs(got - want).max()) / sc
+        del pv, pdep
+        parity = {"n_sample": int(n_s) * world, "oracle": "oracle/tbslas_oracle.c (port), full trees",
+                  "max_abs_err_departure_points": allmax(e_dep),
+                  "max_rel_err_values_at_equal_points": allmax(e_val),
+                  "max_rel_err_vs_oracle": allmax(e_step),
+                  "call_repeatable_bitwise": bool(allmax(0.0 if same_bits else 1.0) == 0.0),
+                  "what": "tbslas_b200_semilag_insitu (the timed call) on device buffers vs the oracle on a "
+                          "strided sample of every rank's arrival points; errors relative to max |value|"}
+
     # the point-array flavour of the same step, device resident (what `value` was before the
     # tree-level call learnt to use the tensor structure of the arrival points)
     step_points()
@@ -356,11 +422,7 @@ def run_b200(args):
         step_points()
     p1.record()
     barrier()
-    pts_ms = p0.elapsed_time(p1) / n_pts_steps
-    if world > 1:
-        t = torch.tensor([pts_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pts_ms = float(t.item())
+    pts_ms = allmax(p0.elapsed_time(p1) / n_pts_steps)
 
     # ---- the other half of the metric: semi-Lagrangian step time of the tree-level call ---
     # tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) entirely on the device: arrival points
@@ -382,12 +444,51 @@ def run_b200(args):
         barrier()
         tot += s0.elapsed_time(s1)
         scratch.update_coeff(con_local.coeff)
-    step_ms = tot / n_step
-    if world > 1:
-        t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t.item())
+    step_ms = allmax(tot / n_step)
     scratch.destroy()
+
+    # ---- every tree Morton-sharded (the reference's layout, north_star): N > 1 only --------
+    sharded = None
+    if world > 1 and args.replicate_velocity and not args.no_sharded:
+        svel = [ctx.tree(workloads.shard_by_splitters(v, splitters, rank)) for v in wl.vel]
+        svel_f = api.NodeFieldFunctor(svel[0]) if len(svel) == 1 else api.FieldSetFunctor(svel, wl.vel_times)
+        svals = torch.empty_like(vals)
+
+        def step_sharded():
+            ctx.check(ctx.lib.tbslas_b200_semilag_insitu(
+                api.C.byref(svel_f.field), None, tcon.h, wl.bc, 1, float(wl.dt), 1, svals.data_ptr(), 1))
+        for _ in range(2):
+            step_sharded()
+        barrier()
+        ctx.profile_reset()
+        ctx.profile_enable(True)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(args.steps):
+            step_sharded()
+        q1.record()
+        barrier()
+        sh_ms = allmax(q0.elapsed_time(q1) / args.steps)
+        sprof = ctx.profile()
+        ctx.profile_enable(False)
+        s_exc = ctx.last_grid_exceptions()
+        sent, recv = ctx.comm_last_exchange()
+        s_sum, s_bits = checksums(svals)
+        mine = {"exchange_ms": round(sprof["Exchange"]["ms"] / args.steps, 3),
+                "unpack_ms": round(sprof["Unpack"]["ms"] / args.steps, 3),
+                "sent_last_eval": sent, "received_last_eval": recv, "grid_exceptions": s_exc,
+                "velocity_leaves_local": svel[0].n_leaf}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        sharded = {"value": n_total / (sh_ms * 1e-3), "unit": "points/s", "ms_per_step": sh_ms,
+                   "checksum_bits": s_bits, "bit_identical_to_replicated_velocity": bool(s_bits == checksum_bits),
+                   "per_rank": gathered,
+                   "what": "the same tree-level step with EVERY tree partitioned by the advected tree's Morton "
+                           "break points (tree_functor.h:433-437,491-596): three collective evaluations per "
+                           "step; the first velocity evaluation still runs by sum factorisation where the "
+                           "containing velocity leaf is local"}
+        for t in svel:
+            t.destroy()
 
     # ---- end to end: pinned host buffers through the C ABI -----------------------------
     h_pos = torch.empty((n_local, 3), dtype=torch.float64, pin_memory=True)
@@ -401,43 +502,41 @@ def run_b200(args):
     step_host()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
+    pa_steps = max(1, min(args.steps, 3))
+    for _ in range(pa_steps):
         step_host()  # returns after the values have landed in host memory
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = allmax((time.perf_counter() - t0) / pa_steps)
     checksum = float(np_vals.sum())
 
     # ---- end to end, tree-level call: what a reference driver does per step through the drop-in
     # adaptor of tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) -- upload the advected tree's
     # coefficients from (pinned) host memory, run the step, read the new grid values back.  No
-    # point ever crosses PCIe: the arrival points are generated in HBM.
+    # point ever crosses PCIe: the arrival points are generated in HBM.  The upload is asynchronous
+    # (tbslas_b200_tree_update_coeff_async): only the third evaluation of the step reads the advected
+    # tree, so the copy hides behind the two velocity evaluations.
     nc = ftm.ncoef(wl.q)
     h_coef = torch.empty((con_local.n_leaf, 1, nc), dtype=torch.float64, pin_memory=True)
     h_coef.copy_(torch.from_numpy(np.ascontiguousarray(con_local.coeff)))
     np_coef = h_coef.numpy()
 
     def step_tree():
-        tcon.update_coeff(np_coef)
+        tcon.update_coeff(np_coef, wait=False)
         ctx.check(ctx.lib.tbslas_b200_semilag_insitu(
             api.C.byref(vel_f.field), None, tcon.h, wl.bc, 1, float(wl.dt), 1, np_vals.ctypes.data, 0))
 
-    step_tree()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(2):
         step_tree()
     barrier()
-    tree_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([tree_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tree_s = float(t.item())
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_tree()  # returns after the values have landed in host memory
+    barrier()
+    tree_s = allmax((time.perf_counter() - t0) / e2e_steps)
     checksum_tree = float(np_vals.sum())
+    h_sum, h_bits = checksums(torch.from_numpy(np_vals))
+    exch_mode = ctx.comm_exchange_mode() if world > 1 else ("none", 0)
 
     if rank != 0:
         if world > 1:
@@ -471,6 +570,7 @@ def run_b200(args):
     roofline = {
         "bound": "fp64", "kernel": "cheb_eval_kernel<q=%d>" % wl.q, "achieved": ach_tf,
         "peak": peak_fp64, "unit": "TFLOP/s", "frac": ach_tf / peak_fp64 if peak_fp64 else None,
+        "frac_nominal": ach_tf / 37.2,
         "peak_source": "measured in this run: DFMA-only kernel, best of 5 (MEASURED_PEAKS.json has "
                        "no FP64 entry; nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2)",
         "flops_model": "reference's own: N*(9d + 2*dof*Ncoef), tree_functor.h:389-394",
@@ -490,39 +590,49 @@ def run_b200(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "%s: %s" % (wl.name, wl.desc), "leaves": wl.con.n_leaf,
-                   "points_total": n_total, "points_per_gpu": n_local, "q": wl.q,
-                   "bc": "periodic" if wl.bc else "freespace", "dt": wl.dt, "nrk": 1,
-                   "velocity_trees": len(tvel), "velocity_leaves": wl.vel[0].n_leaf,
-                   "step": "tbslas_b200_semilag_insitu on device buffers: arrival points generated in HBM, "
-                           "RK2 trajectories, scalar at the departure points",
-                   "velocity_evaluations_per_step": n_eval_vel + (1 if tensor else 0),
-                   "first_velocity_evaluation": None if not tensor else
-                   "sum factorisation over the arrival grids (tensor_eval.cu); %d of %d points per step "
-                   "(on velocity-leaf faces) through the generic kernels" % (n_exc, n_local),
-                   "time_interpolation": None if not combined else
-                   "coefficients of the 4 snapshots (one leaf list) combined in time on the device, one "
-                   "evaluation per RK stage; tbslas_b200_set_time_combine(ctx, 0) evaluates every snapshot",
-                   "l2_policy": "inputs (%.1f GB of points per step) exceed the 126 MB L2" %
-                                (n_local * 24 / 1e9),
-                   "partition": "single GPU" if world == 1 else
-                                "equal-count contiguous Morton ranges of the advected tree; velocity "
-                                + ("tree replicated on every rank (no exchange for velocity evaluations)"
-                                   if args.replicate_velocity else
-                                   "tree re-partitioned with the same break points (whole leaves)"),
-                   "exchange": None if world == 1 else
-                   {"collective": "NCCL all-to-all-v (grouped send/recv), forward xyz + reverse values",
-                    "rank0_last_eval_sent": exch[0], "rank0_last_eval_received": exch[1]}},
+        # the same keys in both arms; how THIS arm ran the workload is in `run_config`
+        "config": dict(workload_config(wl), sample=None),
+        "run_config": dict(
+            points_per_gpu=n_local,
+            step="tbslas_b200_semilag_insitu on device buffers: arrival points generated in HBM, "
+                 "RK2 trajectories, scalar at the departure points",
+            velocity_evaluations_per_step=n_eval_vel + (1 if tensor else 0),
+            first_velocity_evaluation=None if not tensor else
+            "sum factorisation over the arrival grids (tensor_eval.cu); %d of %d points per step "
+            "(on velocity-leaf faces) through the generic kernels" % (n_exc, n_local),
+            time_interpolation=None if not combined else
+            "coefficients of the 4 snapshots (one leaf list) combined in time on the device, one "
+            "evaluation per RK stage; tbslas_b200_set_time_combine(ctx, 0) evaluates every snapshot",
+            l2_policy="inputs (%.1f GB of points per step) exceed the 126 MB L2" % (n_local * 24 / 1e9),
+            partition="single GPU" if world == 1 else
+            "equal-count contiguous Morton ranges of the advected tree; velocity "
+            + ("tree replicated on every rank (no exchange for velocity evaluations)"
+               if args.replicate_velocity else
+               "tree re-partitioned with the same break points (whole leaves)"),
+            exchange=None if world == 1 else
+            {"mode": exch_mode[0], "mailbox_points": exch_mode[1],
+             "what": "peer: outsiders written straight into the owner's receive buffer over NVLink peer "
+                     "memory, values straight back, counts/offsets/barriers on the device (no host "
+                     "synchronisation, no NCCL kernel in the step); nccl: all-to-all-v by grouped "
+                     "ncclSend/ncclRecv" ,
+             "rank0_last_eval_sent": exch[0], "rank0_last_eval_received": exch[1]}),
+        "checksum_global": {"sum": checksum_dev, "bits": checksum_bits,
+                            "what": "over ALL ranks' advected values of the timed step: float sum, and the sum "
+                                    "of the values' 64-bit patterns mod 2^64 (order- and partition-independent: "
+                                    "equal at N = 1, 2, 4, 8 iff the values are bit-identical)"},
+        "parity_check": parity,
         "clocks": clocks, "gpu_launches": int(launches),
         # headline end-to-end number: the tree-level call every reference driver makes
         # (SolveSemilagInSitu, advection.cpp:296) through the C ABI with pinned HOST buffers
         "e2e": {"value": n_total / tree_s, "unit": "points/s", "ms_per_step": tree_s * 1e3,
                 "h2d_bytes_per_step": int(con_local.n_leaf * nc * 8), "d2h_bytes_per_step": int(n_local * 8),
-                "steps": e2e_steps, "checksum": checksum_tree,
-                "what": "tbslas_b200_tree_update_coeff + tbslas_b200_semilag_insitu (SolveSemilagInSitu "
+                "steps": e2e_steps, "checksum": checksum_tree, "checksum_bits": h_bits,
+                "bit_identical_to_device_buffers": bool(h_bits == checksum_bits),
+                "what": "tbslas_b200_tree_update_coeff_async + tbslas_b200_semilag_insitu (SolveSemilagInSitu "
                         "steps 1-2, tree_semilag.h:92-130): the advected tree's coefficients up from pinned "
-                        "host memory, arrival points generated in HBM, advected grid values down to pinned "
-                        "host memory; leaf chunks pipelined (D2H of chunk c-1 under the kernels of chunk c)",
+                        "host memory (under the velocity evaluations), arrival points generated in HBM, advected "
+                        "grid values down to pinned host memory; leaf chunks pipelined (D2H of chunk c-1 under "
+                        "the kernels of chunk c); wall clock over all timed steps",
                 "point_array_call": {
                     "value": n_total / e2e_s, "unit": "points/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(n_local * 24), "d2h_bytes_per_step": int(n_local * 8),
@@ -540,6 +650,8 @@ def run_b200(args):
     }
     if per_rank is not None:
         line["per_rank_stage_ms"] = per_rank
+    if sharded is not None:
+        line["sharded_all_trees"] = sharded
     if world == 1 and not args.no_cpu:
         pts, nl = sample_points(wl, args.cpu_leaves)
         rate, kind, cores, sec = cpu_run(wl, pts, 1, 1)
@@ -680,6 +792,12 @@ def main():
     ap.add_argument("--cpu-leaves", type=int, default=8192,
                     help="leaves in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle sample (parity_check)")
+    ap.add_argument("--parity-points", type=int, default=2048, help="oracle sample per rank")
+    ap.add_argument("--no-sharded", action="store_true",
+                    help="multi-GPU: skip the extra measurement with every tree Morton-sharded")
+    ap.add_argument("--exchange", default=None, choices=["peer", "nccl"],
+                    help="multi-GPU: how outsiders travel (default: peer memory where available)")
     ap.add_argument("--replicate-velocity", action="store_true",
                     help="multi-GPU: every rank holds the whole velocity tree (SURVEY 8(f) row f3); "
                          "default when the velocity trees take <= 1 GiB")

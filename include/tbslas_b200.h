@@ -94,6 +94,23 @@ int tbslas_b200_comm_rank(tbslas_ctx *ctx, int *rank, int *nranks);
 /* Outsider points this rank sent to / received from other ranks during the most recent
  * tree evaluation (the cnt_outside of tree_functor.h:513-517 and its mirror image). */
 int tbslas_b200_comm_last_exchange(tbslas_ctx *ctx, size_t *sent, size_t *received);
+/* How the outsiders travel (par::SortScatterIndex / ScatterForward / ScatterReverse,
+ * tree_functor.h:569-595).
+ *   mode 1 (default where every rank can map every peer's memory -- one NVLink/NVSwitch box):
+ *     peer-memory mailboxes.  The pack kernel writes each outsider straight into its owner's
+ *     receive buffer over NVLink, the owner evaluates what arrived and writes the values straight
+ *     back; counts, offsets and the three barriers of an evaluation live on the device, so an
+ *     evaluation costs no host synchronisation and no library kernel sits next to the
+ *     evaluation kernel.  A rank can receive (and send) at most `mailbox_points` outsiders per
+ *     evaluation (grown at tree_create to a quarter of the largest shard's arrival points;
+ *     comm_set_mailbox -- collective -- sets it); beyond that the evaluation fails with
+ *     TBSLAS_ERR_COMM at the next synchronising call, on every rank.
+ *   mode 0: NCCL all-to-all-v (count matrix by ncclAllGather, grouped ncclSend/ncclRecv both
+ *     ways): no capacity limit, one host synchronisation per evaluation.
+ * All ranks must select the same mode.  comm_exchange_mode reports what is in effect. */
+int tbslas_b200_comm_set_exchange(tbslas_ctx *ctx, int mode);
+int tbslas_b200_comm_set_mailbox(tbslas_ctx *ctx, size_t points);
+int tbslas_b200_comm_exchange_mode(tbslas_ctx *ctx, int *mode, size_t *mailbox_points);
 
 /* ---- trees -------------------------------------------------------------- */
 /* Replaces: the leaf walk at tree_functor.h:417-427 (GetNodeList filtered by
@@ -121,6 +138,14 @@ int tbslas_b200_tree_create_replicated(tbslas_ctx *ctx, int q, int dof, size_t n
 /* New coefficients on the same leaves (what SetTreeGridValues writes every step,
  * tree_utils.h:547-550). */
 int tbslas_b200_tree_update_coeff(tbslas_tree *tree, const double *coeff, int mem);
+/* The same without waiting: the copy runs on the context's copy stream, behind the evaluations
+ * already enqueued that still read the old coefficients and concurrently with whatever is enqueued
+ * next; the first later call that touches this tree's coefficients waits for it ON THE DEVICE.
+ * A host buffer must be pinned for the copy to overlap and must stay valid until a
+ * synchronising call on the context returns (any call with host output buffers, or
+ * tbslas_b200_synchronize).  In a semi-Lagrangian step only the last of the three evaluations
+ * reads the advected tree, so its upload hides behind the two velocity evaluations. */
+int tbslas_b200_tree_update_coeff_async(tbslas_tree *tree, const double *coeff, int mem);
 /* Read the coefficients back, [n_leaf][dof][Ncoef] (e.g. after semilag_insitu_update, before
  * the host refines the tree). */
 int tbslas_b200_tree_get_coeff(tbslas_tree *tree, double *coeff, int mem);
@@ -182,6 +207,11 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2,
  * fewer than 4 Mi points keep the generic path (latency bound either way); mode 2 removes that
  * minimum (tests).  mode 0: every evaluation is point by point. */
 int tbslas_b200_set_tensor_grid(tbslas_ctx *ctx, int mode);
+/* Calls with HOST buffers are cut into chunks whose copy-in, kernels and copy-out overlap on three
+ * streams.  chunks = 0 (default): chosen from the bytes that cross PCIe (about 16 Mi points per chunk
+ * for tree-level calls, 4 Mi with host input, at most 16); > 0: exactly that many.  In a multi-rank
+ * context every rank must use the same setting (every chunk is a collective evaluation). */
+int tbslas_b200_set_host_chunks(tbslas_ctx *ctx, int chunks);
 /* Arrival points of the most recent tree-level call (or of its last chunk, for host buffers) that
  * took the generic path instead (on a velocity-leaf face, or in a leaf not inside one velocity leaf). */
 int tbslas_b200_last_grid_exceptions(tbslas_ctx *ctx, size_t *n);
@@ -193,6 +223,12 @@ int tbslas_b200_last_grid_exceptions(tbslas_ctx *ctx, size_t *n);
 int tbslas_b200_semilag_insitu(const tbslas_field *f1, const tbslas_field *f2,
                                tbslas_tree *con, int bc, int timestep, double dt, int nrk,
                                double *out_vals, int mem);
+
+/* The same, also returning the departure points [n_leaf*(q+1)^3][3] as ComputeTrajRK2 left them
+ * (before the scalar evaluation wraps them): what the parity tests compare stage by stage. */
+int tbslas_b200_semilag_insitu_dep(const tbslas_field *f1, const tbslas_field *f2,
+                                   tbslas_tree *con, int bc, int timestep, double dt, int nrk,
+                                   double *out_vals, double *out_dep, int mem);
 
 /* ---- values -> coefficients: tbslas::SetTreeGridValues (tree_utils.h:500-552) ------ */
 /* The point-to-coefficient matrix of degree q, M[(q+1)^3][Ncoef] row-major (host memory):

@@ -37,16 +37,24 @@ def _is_torch(a) -> bool:
     return torch is not None and isinstance(a, torch.Tensor)
 
 
-def _addr(a, dtype=None):
-    """-> (address, mem) of a C-contiguous numpy array or torch CUDA tensor."""
+def _addr(a, dtype="f64"):
+    """-> (address, mem) of a C-contiguous numpy array or torch CUDA tensor of the element type
+    the C ABI reads ("f64": double, "i32": int32_t).  A float32 array handed to a double* entry
+    point would be read past its end, so the type is checked here, loudly."""
     if a is None:
         return None, None
     if _is_torch(a):
-        assert a.is_cuda and a.is_contiguous(), "device buffers must be contiguous CUDA tensors"
+        want = torch.float64 if dtype == "f64" else torch.int32
+        if not (a.is_cuda and a.is_contiguous()):
+            raise TypeError("device buffers must be contiguous CUDA tensors")
+        if a.dtype != want:
+            raise TypeError("device buffer has dtype %s, the C ABI expects %s" % (a.dtype, want))
         return a.data_ptr(), MEM_DEVICE
-    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"], "host buffers must be C-contiguous numpy"
-    if dtype is not None:
-        assert a.dtype == dtype, (a.dtype, dtype)
+    want = np.float64 if dtype == "f64" else np.int32
+    if not (isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]):
+        raise TypeError("host buffers must be C-contiguous numpy arrays")
+    if a.dtype != want:
+        raise TypeError("host buffer has dtype %s, the C ABI expects %s" % (a.dtype, np.dtype(want)))
     return a.ctypes.data, MEM_HOST
 
 
@@ -129,6 +137,22 @@ class Context:
         self.check(self.lib.tbslas_b200_comm_last_exchange(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def comm_set_exchange(self, mode: str) -> None:
+        """"peer": NVLink peer-memory mailboxes (default where available); "nccl": all-to-all-v."""
+        self.check(self.lib.tbslas_b200_comm_set_exchange(self.h, {"peer": 1, "nccl": 0}[mode]))
+
+    def comm_set_mailbox(self, points: int) -> None:
+        self.check(self.lib.tbslas_b200_comm_set_mailbox(self.h, int(points)))
+
+    def comm_exchange_mode(self):
+        """-> ("peer" | "nccl", mailbox capacity in points)."""
+        m, c = C.c_int(), C.c_size_t()
+        self.check(self.lib.tbslas_b200_comm_exchange_mode(self.h, C.byref(m), C.byref(c)))
+        return ("peer" if m.value else "nccl"), int(c.value)
+
+    def set_host_chunks(self, chunks: int) -> None:
+        self.check(self.lib.tbslas_b200_set_host_chunks(self.h, int(chunks)))
+
     def comm_rank(self):
         r, n = C.c_int(), C.c_int()
         self.check(self.lib.tbslas_b200_comm_rank(self.h, C.byref(r), C.byref(n)))
@@ -204,9 +228,13 @@ class Tree:
                                                   coeff.ctypes.data, MEM_HOST, C.byref(h)))
         self.h = h
 
-    def update_coeff(self, coeff) -> None:
+    def update_coeff(self, coeff, wait: bool = True) -> None:
+        """New coefficients on the same leaves.  wait=False: tbslas_b200_tree_update_coeff_async --
+        the copy overlaps what is enqueued next; the buffer (pinned, if it is to overlap) must stay
+        valid until a synchronising call returns."""
         a, m = _addr(coeff)
-        self.ctx.check(self.ctx.lib.tbslas_b200_tree_update_coeff(self.h, a, m))
+        fn = self.ctx.lib.tbslas_b200_tree_update_coeff if wait else self.ctx.lib.tbslas_b200_tree_update_coeff_async
+        self.ctx.check(fn(self.h, a, m))
 
     def destroy(self) -> None:
         if self.h:
@@ -286,7 +314,7 @@ class NodeFieldFunctor(_Functor):
         leaf = _like(points_pos, (n,), "i32")
         pa, pm = _addr(points_pos)
         self.ctx.check(self.ctx.lib.tbslas_b200_eval(self.tree.h, bc, pa, n, _addr(out)[0],
-                                                     _addr(leaf)[0], pm))
+                                                     _addr(leaf, "i32")[0], pm))
         return out, leaf
 
 
@@ -369,19 +397,29 @@ def SolveSemilagRK2(vel_evaluator: _Functor, con_evaluator: NodeFieldFunctor, po
 
 def SolveSemilagInSitu(tvel_func: _Functor, tree_curr: Tree, timestep: int, dt: float,
                        num_rk_step: int = 1, bc: int = FREESPACE,
-                       tvel_extrap: Optional[_Functor] = None, device: bool = False):
+                       tvel_extrap: Optional[_Functor] = None, device: bool = False,
+                       departure_points: bool = False, out=None):
     """Steps (1)+(2) of tbslas::SolveSemilagInSitu (tree_semilag.h:92-130): the arrival points
     are generated in HBM from ``tree_curr``'s own leaves and advected; returns the new grid
-    values [n_leaf*(q+1)^3, dof] (leaf-major), the input of SetTreeGridValues."""
+    values [n_leaf*(q+1)^3, dof] (leaf-major), the input of SetTreeGridValues -- and, with
+    ``departure_points``, also the departure points [n_leaf*(q+1)^3, 3]."""
     n = tree_curr.n_leaf * (tree_curr.q + 1) ** 3
-    out = (torch.empty((n, tree_curr.dof), dtype=torch.float64, device="cuda:%d" % tree_curr.ctx.device)
-           if device else np.empty((n, tree_curr.dof)))
+    dev = "cuda:%d" % tree_curr.ctx.device
+    if out is None:
+        out = (torch.empty((n, tree_curr.dof), dtype=torch.float64, device=dev)
+               if device else np.empty((n, tree_curr.dof)))
     a, m = _addr(out)
     ctx = tree_curr.ctx
-    ctx.check(ctx.lib.tbslas_b200_semilag_insitu(
-        C.byref(tvel_func.field), C.byref(tvel_extrap.field) if tvel_extrap is not None else None,
-        tree_curr.h, bc, int(timestep), float(dt), int(num_rk_step), a, m))
-    return out
+    f1 = C.byref(tvel_func.field)
+    f2 = C.byref(tvel_extrap.field) if tvel_extrap is not None else None
+    if not departure_points:
+        ctx.check(ctx.lib.tbslas_b200_semilag_insitu(f1, f2, tree_curr.h, bc, int(timestep), float(dt),
+                                                     int(num_rk_step), a, m))
+        return out
+    dep = (torch.empty((n, 3), dtype=torch.float64, device=dev) if m == MEM_DEVICE else np.empty((n, 3)))
+    ctx.check(ctx.lib.tbslas_b200_semilag_insitu_dep(f1, f2, tree_curr.h, bc, int(timestep), float(dt),
+                                                     int(num_rk_step), a, _addr(dep)[0], m))
+    return out, dep
 
 
 def SolveSemilagInSituUpdate(tvel_func: _Functor, tree_curr: Tree, timestep: int, dt: float,

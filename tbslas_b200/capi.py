@@ -23,11 +23,12 @@ SYMBOLS = [
     "tbslas_b200_init", "tbslas_b200_finalize", "tbslas_b200_set_stream",
     "tbslas_b200_synchronize", "tbslas_b200_set_time_combine", "tbslas_b200_cubic_time_weights", "tbslas_b200_set_tensor_grid", "tbslas_b200_last_grid_exceptions", "tbslas_b200_last_error", "tbslas_b200_version",
     "tbslas_b200_comm_unique_id", "tbslas_b200_comm_init", "tbslas_b200_comm_rank",
-    "tbslas_b200_comm_last_exchange",
+    "tbslas_b200_comm_last_exchange", "tbslas_b200_comm_set_exchange", "tbslas_b200_comm_set_mailbox",
+    "tbslas_b200_comm_exchange_mode", "tbslas_b200_tree_update_coeff_async", "tbslas_b200_set_host_chunks",
     "tbslas_b200_tree_create", "tbslas_b200_tree_create_replicated", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_get_coeff", "tbslas_b200_tree_destroy",
     "tbslas_b200_tree_info", "tbslas_b200_eval", "tbslas_b200_eval_set4",
     "tbslas_b200_eval_extrap", "tbslas_b200_eval_field", "tbslas_b200_traj_rk2",
-    "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_set_pt2coeff",
+    "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_semilag_insitu_dep", "tbslas_b200_set_pt2coeff",
     "tbslas_b200_tree_set_grid_values", "tbslas_b200_semilag_insitu_update", "tbslas_b200_cubic_eval", "tbslas_b200_collect_grid_points",
     "tbslas_b200_new_nodes", "tbslas_b200_point_key", "tbslas_b200_owner_of_key",
     "tbslas_b200_partition_leaves", "tbslas_b200_partition_leaves_weighted",
@@ -76,6 +77,11 @@ def load() -> C.CDLL:
     L.tbslas_b200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.tbslas_b200_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tbslas_b200_comm_last_exchange.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+    L.tbslas_b200_comm_set_exchange.argtypes = [vp, C.c_int]
+    L.tbslas_b200_comm_set_mailbox.argtypes = [vp, sz]
+    L.tbslas_b200_comm_exchange_mode.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(sz)]
+    L.tbslas_b200_set_host_chunks.argtypes = [vp, C.c_int]
+    L.tbslas_b200_tree_update_coeff_async.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_tree_create.argtypes = [vp, C.c_int, C.c_int, sz, dp, vp, dp, C.c_int,
                                           C.POINTER(vp)]
     L.tbslas_b200_tree_create_replicated.argtypes = L.tbslas_b200_tree_create.argtypes
@@ -96,6 +102,8 @@ def load() -> C.CDLL:
                                           sz, C.c_int, C.c_double, C.c_int, dp, dp, C.c_int]
     L.tbslas_b200_semilag_insitu.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int,
                                              C.c_int, C.c_double, C.c_int, dp, C.c_int]
+    L.tbslas_b200_semilag_insitu_dep.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int,
+                                                 C.c_int, C.c_double, C.c_int, dp, dp, C.c_int]
     L.tbslas_b200_set_pt2coeff.argtypes = [vp, C.c_int, dp]
     L.tbslas_b200_tree_set_grid_values.argtypes = [vp, dp, C.c_int, C.c_int]
     L.tbslas_b200_semilag_insitu_update.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int,

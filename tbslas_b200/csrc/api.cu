@@ -92,6 +92,12 @@ int comm_begin_exchange(tbslas_ctx *ctx, const uint32_t *send_count_dev);
 int comm_forward_exchange(tbslas_tree *t, const double *send_pos, bool want_leaf);
 int comm_finish_exchange(tbslas_tree *t, int bc, const uint32_t *send_idx, int epilogue, double *out,
                          const double *base, double alpha, int32_t *leaf_out);
+bool comm_peer_exchange(tbslas_ctx *ctx);
+int comm_check(tbslas_ctx *ctx);
+int px_begin(tbslas_tree *t, const uint32_t *send_count_dev, PxPack *pack);
+int px_packed(tbslas_ctx *ctx);
+int px_finish(tbslas_tree *t, int bc, const uint32_t *send_idx, size_t n_local, int epilogue, double *out,
+              const double *base, double alpha, int32_t *leaf_out);
 void comm_destroy(tbslas_ctx *ctx);
 
 // ---------------------------------------------------------------------------
@@ -102,13 +108,27 @@ void comm_destroy(tbslas_ctx *ctx);
 // only the evaluation kernel runs (the four snapshots of a FieldSetFunctor, the two trees of
 // a FieldExtrapFunctor -- the reference sorts and searches once per tree).
 static bool same_leaves(const tbslas_tree *a, const tbslas_tree *b) {
+  // equal degree and block stride too: the combined-coefficient route reads every tree's blocks
+  // with tree[0]'s layout (trees of different degree take the per-tree route, like the reference)
   return a && b && a->ctx == b->ctx && a->n_leaf == b->n_leaf && a->struct_hash == b->struct_hash &&
+         a->global_hash == b->global_hash && a->q == b->q && a->stride == b->stride &&
          eval_tile_points(a) == eval_tile_points(b) && eval_needs_tile_map(a) == eval_needs_tile_map(b);
 }
 
+int tree_coeff_ready(const tbslas_tree *ct) {
+  tbslas_tree *t = const_cast<tbslas_tree *>(ct);
+  if (!t->coeff_pending) return TBSLAS_OK;
+  TB_CUDA(t->ctx, cudaStreamWaitEvent(t->ctx->stream, t->ev_coeff, 0));
+  t->coeff_pending = false;
+  return TBSLAS_OK;
+}
+
+// `n_dev` != nullptr: the number of points is known on the device only (points that arrived through
+// the peer-exchange mailbox); n is then the capacity that sizes workspaces and grids.
 static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int epilogue,
                              double *out, const double *base, double alpha, int32_t *leaf_out,
-                             bool allow_exchange, const tbslas_tree *same_as = nullptr) {
+                             bool allow_exchange, const tbslas_tree *same_as = nullptr,
+                             const uint32_t *n_dev = nullptr) {
   tbslas_ctx *ctx = t->ctx;
   if (n >= (size_t)0xfffffff0u)
     return fail(ctx, TBSLAS_ERR_INVALID, "n = %zu exceeds the 32-bit point index range", n);
@@ -118,6 +138,7 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   if (tile_pts <= 0)
     return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "Chebyshev degree %d not supported (1..%d)", t->q,
                 TBSLAS_MAX_CHEB_DEG);
+  TB_TRY(tree_coeff_ready(t));
   const size_t max_tiles = n / tile_pts + t->n_leaf + 2;
   void *leaf, *rank, *count, *bin_start, *tile_start, *tile_map = nullptr, *perm, *send_count = nullptr;
   void *send_pos = nullptr, *send_idx = nullptr;
@@ -129,15 +150,16 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   TB_TRY(ws_get(ctx, WS_TILESTART, sizeof(uint32_t) * (t->n_leaf + 2), &tile_start));
   if (eval_needs_tile_map(t)) TB_TRY(ws_get(ctx, WS_TILELEAF, sizeof(int2) * max_tiles, &tile_map));
   const bool multi = allow_exchange && ctx->nranks > 1 && !t->replicated;
+  const bool peer = multi && comm_peer_exchange(ctx);
   if (multi) {
     send_count = (uint32_t *)count + t->n_leaf + 2;
     // worst case: every point is an outsider (sizes must be known before the counts are)
-    TB_TRY(ws_get(ctx, WS_SEND, sizeof(double) * 3 * (n + 1), &send_pos));
+    if (!peer) TB_TRY(ws_get(ctx, WS_SEND, sizeof(double) * 3 * (n + 1), &send_pos));
     TB_TRY(ws_get(ctx, WS_SENDIDX, sizeof(uint32_t) * (n + 1), &send_idx));
   }
 
   static const bool exchange_first = !(getenv("TBSLAS_EXCHANGE_FIRST") && atoi(getenv("TBSLAS_EXCHANGE_FIRST")) == 0);
-  const bool reuse = !multi && !leaf_out && same_leaves(t, same_as) &&
+  const bool reuse = !multi && !leaf_out && !n_dev && same_leaves(t, same_as) &&
                      !(same_as->ctx->nranks > 1 && !same_as->replicated);
   if (reuse) {  // the persistent evaluation kernel's work counter is the one thing to reset
     TB_CUDA(ctx, cudaMemsetAsync((uint32_t *)count + t->n_leaf + 2 + kMaxRanks, 0, sizeof(uint32_t), ctx->stream));
@@ -147,16 +169,22 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
     la.periodic = (bc == TBSLAS_PERIODIC);
     la.pos = pos;
     la.n = n;
+    la.n_dev = n_dev;
     la.leaf = (int32_t *)leaf;
     la.rank = (uint32_t *)rank;
     la.count = (uint32_t *)count;
     la.send_count = (uint32_t *)send_count;
     TB_TRY(launch_locate(ctx, la));
-    if (multi) TB_TRY(comm_begin_exchange(ctx, (const uint32_t *)send_count));
+    PxPack pack;
+    if (peer)
+      TB_TRY(px_begin(t, (const uint32_t *)send_count, &pack));
+    else if (multi)
+      TB_TRY(comm_begin_exchange(ctx, (const uint32_t *)send_count));
 
     BinArgs ba;
     ba.n_leaf = t->n_leaf;
     ba.n = n;
+    ba.n_dev = n_dev;
     ba.tile_pts = tile_pts;
     ba.leaf = (const int32_t *)leaf;
     ba.rank = (const uint32_t *)rank;
@@ -172,12 +200,17 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
       ba.nranks = ctx->nranks;
       ba.send_pos = (double *)send_pos;
       ba.send_idx = (uint32_t *)send_idx;
+      if (peer) ba.px = &pack;
     }
     TB_TRY(launch_bin(ctx, ba));
-    // The persistent evaluation kernel fills every SM, so an NCCL kernel enqueued behind it on
-    // another stream could not start before it drains; posting the forward exchange FIRST lets the
-    // outsiders travel while the insiders are evaluated (TBSLAS_EXCHANGE_FIRST=0: old order).
-    if (multi) {
+    if (peer) {
+      // the outsiders are in their owners' mailboxes: say so, then evaluate the insiders while the
+      // peers' points arrive
+      TB_TRY(px_packed(ctx));
+    } else if (multi) {
+      // The persistent evaluation kernel fills every SM, so an NCCL kernel enqueued behind it on
+      // another stream could not start before it drains; posting the forward exchange FIRST lets the
+      // outsiders travel while the insiders are evaluated (TBSLAS_EXCHANGE_FIRST=0: old order).
       TB_CUDA(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
       if (exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
     }
@@ -192,7 +225,7 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   EvalArgs ea;
   ea.tree = t;
   ea.pos = pos;
-  ea.n = n;
+  ea.n = n_dev ? 0 : n;
   ea.perm = (const uint32_t *)perm;
   ea.bin_start = (const uint32_t *)bin_start;
   ea.tile_start = (const uint32_t *)tile_start;
@@ -210,7 +243,9 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
                                  ctx->stream));
     TB_TRY(launch_leaf_fixup(ctx, leaf_out, n, t->n_leaf, t->leaf_offset));
   }
-  if (multi) {
+  if (peer) {
+    TB_TRY(px_finish(t, bc, (const uint32_t *)send_idx, n, epilogue, out, base, alpha, leaf_out));
+  } else if (multi) {
     if (!exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
     TB_TRY(comm_finish_exchange(t, bc, (const uint32_t *)send_idx, epilogue, out, base, alpha, leaf_out));
   }
@@ -223,9 +258,9 @@ int eval_tree_dev_points(tbslas_tree *t, int bc, double *pos, size_t n, double *
 }
 
 // used by comm.cu to evaluate points received from other ranks (all of them local)
-int eval_received_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out,
+int eval_received_points(tbslas_tree *t, int bc, double *pos, size_t n, const uint32_t *n_dev, double *out,
                          int32_t *leaf_out) {
-  return eval_local_points(t, bc, pos, n, EPI_STORE, out, nullptr, 0.0, leaf_out, false);
+  return eval_local_points(t, bc, pos, n, EPI_STORE, out, nullptr, 0.0, leaf_out, false, nullptr, n_dev);
 }
 
 static int eval_tree_dev(tbslas_tree *t, int bc, double *pos, size_t n, int epilogue, double *out,
@@ -281,6 +316,7 @@ static int field_single_tree(tbslas_ctx *ctx, const tbslas_field *f, double tq, 
   const size_t mc = (t0->n_leaf + 1) * t0->stride;
   void *cc;
   TB_TRY(ws_get(ctx, WS_COEF, sizeof(double) * mc, &cc));
+  for (int i = 0; i < nt; i++) TB_TRY(tree_coeff_ready(f->tree[i]));
   const double *src[4] = {f->tree[0]->d_coeff, f->tree[1]->d_coeff, nt == 4 ? f->tree[2]->d_coeff : nullptr,
                           nt == 4 ? f->tree[3]->d_coeff : nullptr};
   TB_TRY(launch_combine_coeff(ctx, src, w, nt, mc, (double *)cc));
@@ -333,7 +369,8 @@ static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos,
 // (tensor_eval.cu) wherever that applies.
 static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, double *xsol,
                         double *xtmp, size_t n, double tinit, double tfinal, int nrk,
-                        const double *x0 = nullptr, const tbslas_tree *grid = nullptr, size_t leaf0 = 0) {
+                        const double *x0 = nullptr, const tbslas_tree *grid = nullptr, size_t leaf0 = 0,
+                        bool gen_points = false) {
   const double tau = (tfinal - tinit) / nrk;  // traj.inc:55
   double tcur = tinit;
   tbslas_ctx *ctx = f1->tree[0]->ctx;
@@ -346,18 +383,24 @@ static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, 
     double *x = (s == 0 && x0) ? const_cast<double *>(x0) : xsol;  // not written unless periodic
     // v1 = V(x, t);  xtmp = x + 0.5*tau*v1      traj.inc:33-36 (x wrapped in place if periodic)
     bool done = false;
-    // (small point sets are latency bound either way and the shortcut costs a host-visible count)
-    if (s == 0 && grid && ctx->tensor_grid && x == xsol && n >= ctx->tensor_grid_min_points) {
+    if (s == 0 && grid && x == xsol) {
       const size_t P = (size_t)(grid->q + 1) * (grid->q + 1) * (grid->q + 1);
-      tbslas_tree view, *one = nullptr;
-      TB_TRY(field_single_tree(ctx, f1, tcur, &view, &one));
-      if (one && n % P == 0) {
-        const int rc = launch_tensor_grid_eval(ctx, one, grid, leaf0, n / P, bc, x, xtmp, 0.5 * tau);
-        if (rc == TBSLAS_OK)
-          done = true;
-        else if (rc != TBSLAS_ERR_UNSUPPORTED)
-          return rc;
+      // small point sets are latency bound either way; a Morton-sharded velocity tree makes the
+      // shortcut's generic pass a collective, so there the choice must not depend on this rank's n
+      const bool sharded = ctx->nranks > 1 && !f1->tree[0]->replicated;
+      if (ctx->tensor_grid && (n >= ctx->tensor_grid_min_points || sharded) && n % P == 0) {
+        tbslas_tree view, *one = nullptr;
+        TB_TRY(field_single_tree(ctx, f1, tcur, &view, &one));
+        if (one) {
+          const int rc = launch_tensor_grid_eval(ctx, one, grid, leaf0, n / P, bc, x, xtmp, 0.5 * tau, gen_points);
+          if (rc == TBSLAS_OK)
+            done = true;
+          else if (rc != TBSLAS_ERR_UNSUPPORTED)
+            return rc;
+        }
       }
+      // `gen_points`: the start points are still to be written (CollectChebTreeGridPoints)
+      if (!done && gen_points && n) TB_TRY(launch_grid_points(ctx, grid, x, leaf0, n / P));
     }
     if (!done) TB_TRY(eval_field_dev(f1, tcur, bc, x, n, xtmp, 1, x, 0.5 * tau));
     // v2 = V(xtmp, t + tau/2);  x = x + tau*v2  traj.inc:40-42
@@ -396,7 +439,7 @@ struct HostIO {  // staging of caller buffers that live in host memory
   int finish() {
     if (mem == TBSLAS_MEM_DEVICE) return TBSLAS_OK;
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return TBSLAS_OK;
+    return comm_check(ctx);
   }
 };
 
@@ -424,27 +467,31 @@ struct PipeSpec {
   int32_t *h_leaf = nullptr;      // [n], optional
   bool need_tmp = false;
   size_t unit = 1;                // chunks are whole multiples of `unit` points (a leaf's grid)
+  size_t n_collective = 0;        // multi-rank: a point count every rank knows (0: none)
 };
 enum { EV_IN = 0, EV_A, EV_POSOUT, EV_B, EV_OUT };
 
-static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char *e = getenv("TBSLAS_HOST_CHUNKS");
-    forced = e ? atoi(e) : 0;
+// Chunks of a host-buffer call.  What is exposed is the copy-in of the first chunk (calls with host
+// input) and the copy-out of the last one, so chunks should be small; what a chunk costs is a few
+// launches' worth of ramp-up and tail of the persistent kernels, so not too small: about 16 Mi
+// points (128 MB of values, ~2.5 ms of PCIe) per chunk for tree-level calls, 4 Mi with host input,
+// never more than 16 chunks.  `n_collective`: in a multi-rank context every chunk is a collective
+// evaluation, so the count must be the same on every rank: it is derived from a size all ranks
+// know (the largest shard's arrival points for tree-level calls) or is the fixed 8.
+static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input, size_t n_collective) {
+  if (ctx->host_chunks > 0) return ctx->host_chunks;
+  if (ctx->nranks > 1) {
+    if (!n_collective) return 8;
+    n = n_collective;
   }
-  if (forced > 0) return forced;
-  if (ctx->nranks > 1) return 8;
-  const size_t k = n >> 20;  // >= 1 Mi points per chunk
-  // with host input the first chunk's copy is exposed, so chunks are small; without (tree-level
-  // calls) only the last chunk's copy-out is, and every chunk costs a host-visible count
-  const size_t kmax = has_input ? 16 : 8;
-  return (int)(k < 1 ? 1 : (k > kmax ? kmax : k));
+  const size_t per = has_input ? ((size_t)4 << 20) : ((size_t)16 << 20);
+  const size_t k = (n + per / 2) / per;
+  return (int)(k < 1 ? 1 : (k > 16 ? 16 : k));
 }
 
 template <class FA, class FB>
 static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA phase_a, FB phase_b) {
-  const int K = pipe_chunks(ctx, n, sp.h_pos != nullptr);
+  const int K = pipe_chunks(ctx, n, sp.h_pos != nullptr, sp.n_collective);
   const size_t unit = sp.unit ? sp.unit : 1;
   const size_t chunk = ((n / unit + K - 1) / K) * unit + (n % unit ? unit : 0);
   PipeBufs bufs[2] = {};
@@ -510,7 +557,7 @@ static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA p
   }
   TB_CUDA(ctx, cudaStreamSynchronize(s_out));
   TB_CUDA(ctx, cudaStreamSynchronize(s_run));
-  return TBSLAS_OK;
+  return comm_check(ctx);
 }
 
 }  // namespace tb
@@ -540,11 +587,22 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
     return TBSLAS_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
-  cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
+  bool ok = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
   for (auto &pair : ctx->ev_pipe)
-    for (cudaEvent_t &e : pair) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-  cudaHostAlloc(&ctx->h_counts, sizeof(unsigned) * kMaxRanks * kMaxRanks, cudaHostAllocMapped | cudaHostAllocPortable);  // device-writable (tensor_eval.cu)
+    for (cudaEvent_t &e : pair) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  // device-writable pinned words: the exchange's count matrix (comm.cu) and, separately, the
+  // tensor-grid exception count (tensor_eval.cu)
+  const bool pinned = ok &&
+      cudaHostAlloc(&ctx->h_counts, sizeof(unsigned) * kMaxRanks * kMaxRanks,
+                    cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+      cudaHostAlloc(&ctx->h_exc, sizeof(unsigned) * 16, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
+  if (!ok || !pinned) {
+    const int rc = ok ? TBSLAS_ERR_NOMEM : TBSLAS_ERR_CUDA;
+    cudaGetLastError();
+    tbslas_b200_finalize(ctx);
+    return rc;
+  }
   *out = ctx;
   return TBSLAS_OK;
 }
@@ -552,7 +610,7 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
 int tbslas_b200_finalize(tbslas_ctx *ctx) {
   if (!ctx) return TBSLAS_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   comm_destroy(ctx);
   for (Buf &b : ctx->ws)
     if (b.p) cudaFree(b.p);
@@ -562,6 +620,7 @@ int tbslas_b200_finalize(tbslas_ctx *ctx) {
   }
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->h_exc) cudaFreeHost(ctx->h_exc);
   for (Pt2Coeff &m : ctx->pt2coeff)
     if (m.d_M) cudaFree(m.d_M);
   for (auto &pair : ctx->ev_pipe)
@@ -569,7 +628,7 @@ int tbslas_b200_finalize(tbslas_ctx *ctx) {
       if (e) cudaEventDestroy(e);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
-  cudaStreamDestroy(ctx->own_stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return TBSLAS_OK;
 }
@@ -593,6 +652,12 @@ int tbslas_b200_last_grid_exceptions(tbslas_ctx *ctx, size_t *n) {
   return TBSLAS_OK;
 }
 
+int tbslas_b200_set_host_chunks(tbslas_ctx *ctx, int chunks) {
+  if (!ctx || chunks < 0 || chunks > 1024) return TBSLAS_ERR_INVALID;
+  ctx->host_chunks = chunks;
+  return TBSLAS_OK;
+}
+
 int tbslas_b200_set_tensor_grid(tbslas_ctx *ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return TBSLAS_ERR_INVALID;
   ctx->tensor_grid = mode != 0;
@@ -603,7 +668,7 @@ int tbslas_b200_set_tensor_grid(tbslas_ctx *ctx, int mode) {
 int tbslas_b200_synchronize(tbslas_ctx *ctx) {
   if (!ctx) return TBSLAS_ERR_INVALID;
   TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return TBSLAS_OK;
+  return comm_check(ctx);
 }
 
 const char *tbslas_b200_last_error(tbslas_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -696,6 +761,7 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   TB_TREE_CUDA(cudaMalloc(&t->d_box, sizeof(uint4) * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMemcpy(t->d_box, hb.data(), sizeof(uint4) * (n_leaf + 1), cudaMemcpyHostToDevice));
   t->boxes_ok = boxes_ok;
+  t->boxes_all = boxes_ok;
   {  // cell table: depth g with about two cells per leaf, 1 <= g <= 6 (1 MiB)
     int g = 1;
     while (g < 6 && ((size_t)1 << (3 * g)) < 2 * n_leaf) g++;
@@ -719,7 +785,9 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
       h = (h ^ hd[j]) * 1099511628211ull;
     }
     t->struct_hash = h;
+    t->global_hash = h;
   }
+  t->n_leaf_max = n_leaf;
   TB_TREE_CUDA(cudaMalloc(&t->d_coeff, sizeof(double) * t->stride * (n_leaf + 1)));
   TB_TREE_CUDA(cudaMemcpy(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice));
   TB_TREE_CUDA(cudaMemcpy(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice));
@@ -737,21 +805,43 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
   return TBSLAS_OK;
 }
 
-int tbslas_b200_tree_update_coeff(tbslas_tree *t, const double *coeff, int mem) {
-  if (!t || !coeff) return TBSLAS_ERR_INVALID;
+// [leaf][dof][Ncoef] -> rows padded to an even number of doubles (one flat copy when Ncoef is
+// even already: a pitched copy is one DMA descriptor per 5 KB row)
+static int copy_coeff_in(tbslas_tree *t, const double *coeff, int mem, cudaStream_t s) {
   tbslas_ctx *ctx = t->ctx;
   const size_t ncoef_pad = t->stride / t->dof;
-  StageScope sc(ctx, ST_H2D, (double)(t->n_leaf * t->dof * t->ncoef * 8), 0);
-  // [leaf][dof][Ncoef] -> rows padded to an even number of doubles (one flat copy when Ncoef is
-  // even already: a pitched copy is one DMA descriptor per 5 KB row)
   const cudaMemcpyKind kind = mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (ncoef_pad == t->ncoef)
-    TB_CUDA(ctx, cudaMemcpyAsync(t->d_coeff, coeff, sizeof(double) * t->ncoef * t->n_leaf * t->dof, kind,
-                                 ctx->stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(t->d_coeff, coeff, sizeof(double) * t->ncoef * t->n_leaf * t->dof, kind, s));
   else
     TB_CUDA(ctx, cudaMemcpy2DAsync(t->d_coeff, ncoef_pad * sizeof(double), coeff, t->ncoef * sizeof(double),
-                                   t->ncoef * sizeof(double), t->n_leaf * t->dof, kind, ctx->stream));
+                                   t->ncoef * sizeof(double), t->n_leaf * t->dof, kind, s));
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_tree_update_coeff(tbslas_tree *t, const double *coeff, int mem) {
+  if (!t || (t->n_leaf && !coeff)) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  if (!t->n_leaf) return TBSLAS_OK;
+  TB_TRY(tree_coeff_ready(t));  // an earlier asynchronous upload lands first
+  StageScope sc(ctx, ST_H2D, (double)(t->n_leaf * t->dof * t->ncoef * 8), 0);
+  TB_TRY(copy_coeff_in(t, coeff, mem, ctx->stream));
   if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_tree_update_coeff_async(tbslas_tree *t, const double *coeff, int mem) {
+  if (!t || (t->n_leaf && !coeff)) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  if (!t->n_leaf) return TBSLAS_OK;
+  if (!t->ev_coeff) TB_CUDA(ctx, cudaEventCreateWithFlags(&t->ev_coeff, cudaEventDisableTiming));
+  // readers of the old coefficients already enqueued on the context's stream finish first
+  TB_CUDA(ctx, cudaEventRecord(t->ev_coeff, ctx->stream));
+  TB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, t->ev_coeff, 0));
+  ctx->acc_units[ST_H2D] += (double)(t->n_leaf * t->dof * t->ncoef * 8);
+  TB_TRY(copy_coeff_in(t, coeff, mem, ctx->copy_in));
+  TB_CUDA(ctx, cudaEventRecord(t->ev_coeff, ctx->copy_in));
+  t->coeff_pending = true;
   return TBSLAS_OK;
 }
 
@@ -759,6 +849,7 @@ int tbslas_b200_tree_get_coeff(tbslas_tree *t, double *coeff, int mem) {
   if (!t || (t->n_leaf && !coeff)) return TBSLAS_ERR_INVALID;
   tbslas_ctx *ctx = t->ctx;
   if (!t->n_leaf) return TBSLAS_OK;
+  TB_TRY(tree_coeff_ready(t));
   const size_t ncoef_pad = t->stride / t->dof;
   StageScope sc(ctx, ST_D2H, (double)(t->n_leaf * t->dof * t->ncoef * 8), 0);
   const cudaMemcpyKind kind = mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -775,6 +866,8 @@ int tbslas_b200_tree_get_coeff(tbslas_tree *t, double *coeff, int mem) {
 int tbslas_b200_tree_destroy(tbslas_tree *t) {
   if (!t) return TBSLAS_ERR_INVALID;
   cudaStreamSynchronize(t->ctx->stream);
+  if (t->coeff_pending) cudaStreamSynchronize(t->ctx->copy_in);
+  if (t->ev_coeff) cudaEventDestroy(t->ev_coeff);
   cudaFree(t->d_key);
   cudaFree(t->d_geom);
   cudaFree(t->d_depth);
@@ -912,7 +1005,7 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
         [&](PipeBufs &B, size_t m, size_t) { return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk); },
         [&](PipeBufs &B, size_t m, size_t) { return eval_tree_dev(con, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, nullptr); });
   }
-  if (mem == TBSLAS_MEM_HOST && insitu && n) {
+  if (mem == TBSLAS_MEM_HOST && insitu && (n || (ctx->nranks > 1 && !con->replicated))) {
     // arrival points generated per chunk of leaves in HBM; the values of chunk c-1 travel to the
     // host while chunk c is computed
     const size_t P = (size_t)(con->q + 1) * (con->q + 1) * (con->q + 1);
@@ -922,11 +1015,11 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
     sp.val_dof = con->dof;
     sp.need_tmp = true;
     sp.unit = P;
+    sp.n_collective = con->n_leaf_max * P;
     return run_host_pipeline(
         ctx, sp, n,
         [&](PipeBufs &B, size_t m, size_t off) {
-          TB_TRY(launch_grid_points(ctx, con, B.pos, off / P, m / P));
-          return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk, B.pos, con, off / P);
+          return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk, B.pos, con, off / P, true);
         },
         [&](PipeBufs &B, size_t m, size_t) { return eval_tree_dev(con, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, nullptr); });
   }
@@ -938,11 +1031,8 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
     TB_TRY(ws_get(ctx, WS_POS_A, sizeof(double) * 3 * n, &xsol));
   TB_TRY(ws_get(ctx, WS_POS_B, sizeof(double) * 3 * n, &xtmp));
   TB_TRY(io.out_buf(WS_VAL_B, out_vals, sizeof(double) * con->dof * n, &dval));
-  if (insitu) {
-    if (n) TB_TRY(launch_grid_points(ctx, con, (double *)xsol));
-  }
   TB_TRY(traj_rk2_dev(f1, f2, bc, (double *)xsol, (double *)xtmp, n, tinit, tfinal, nrk,
-                      insitu ? (const double *)xsol : pos, insitu ? con : nullptr, 0));
+                      insitu ? (const double *)xsol : pos, insitu ? con : nullptr, 0, insitu));
   if (mem == TBSLAS_MEM_DEVICE && out_dep && bc == TBSLAS_PERIODIC) {
     // keep the caller's departure points un-wrapped: evaluate on a copy
     TB_CUDA(ctx, cudaMemcpyAsync(xtmp, xsol, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice,
@@ -970,6 +1060,11 @@ int tbslas_b200_semilag_insitu(const tbslas_field *f1, const tbslas_field *f2, t
   return semilag_impl(f1, f2, con, bc, nullptr, 0, timestep, dt, nrk, out_vals, nullptr, mem);
 }
 
+int tbslas_b200_semilag_insitu_dep(const tbslas_field *f1, const tbslas_field *f2, tbslas_tree *con, int bc,
+                                   int timestep, double dt, int nrk, double *out_vals, double *out_dep, int mem) {
+  return semilag_impl(f1, f2, con, bc, nullptr, 0, timestep, dt, nrk, out_vals, out_dep, mem);
+}
+
 // ---------------------------------------------------------------- values -> coefficients
 int tbslas_b200_set_pt2coeff(tbslas_ctx *ctx, int q, const double *M) {
   if (!ctx || !M) return TBSLAS_ERR_INVALID;
@@ -981,6 +1076,7 @@ int tbslas_b200_tree_set_grid_values(tbslas_tree *t, const double *vals, int poi
   if (!t || (t->n_leaf && !vals)) return TBSLAS_ERR_INVALID;
   tbslas_ctx *ctx = t->ctx;
   const size_t d = t->q + 1, m = t->n_leaf * t->dof * d * d * d;
+  TB_TRY(tree_coeff_ready(t));
   HostIO io{ctx, mem};
   void *dv;
   TB_TRY(io.h2d(WS_VAL_A, vals, sizeof(double) * m, &dv));
@@ -1098,6 +1194,7 @@ int tbslas_b200_tree_tail_norm(tbslas_tree *t, double *tail, int mem) {
   if (!t || (t->n_leaf && !tail)) return TBSLAS_ERR_INVALID;
   tbslas_ctx *ctx = t->ctx;
   if (!t->n_leaf) return TBSLAS_OK;
+  TB_TRY(tree_coeff_ready(t));
   HostIO io{ctx, mem};
   void *d;
   TB_TRY(io.out_buf(WS_VAL_A, tail, sizeof(double) * t->n_leaf, &d));

@@ -85,6 +85,21 @@ struct ProfRec {
   double units;
 };
 
+struct ExcCount {  // see tbslas_ctx::exc_cache
+  uint64_t vel_hash, grid_hash;
+  size_t vel_leaves, grid_leaves, leaf0, n_leaf;
+  int q, periodic;
+  size_t count;
+};
+
+struct ExchangeState;  // comm.cu
+struct PxPack {  // where the pack kernel puts outsiders in peer-exchange mode (comm.cu)
+  const uint32_t *send_off = nullptr;  // [nranks] my buckets in my own send order (device)
+  const uint32_t *dst_off = nullptr;   // [nranks] where my bucket starts in the owner's receive buffer
+  char *const *peer_base = nullptr;    // [nranks] mapped mailboxes (device table)
+  size_t off_recv_pos = 0;
+};
+
 }  // namespace tb
 
 struct tbslas_ctx {
@@ -121,8 +136,19 @@ struct tbslas_ctx {
   int tensor_grid = 1;
   size_t tensor_grid_min_points = (size_t)4 << 20;  // tbslas_b200_set_tensor_grid(ctx, 2): no minimum
   size_t last_exceptions = 0;  // arrival points of the last such call that took the generic path
-  // pinned host scratch for small device->host reads (exchange counts: [nranks][nranks])
+  // How many arrival points of a (grid leaf range, velocity tree) pair take the generic path is a
+  // property of the two leaf lists and the boundary condition alone, so it is read back from the
+  // device ONCE per pair and remembered: steps on unchanged trees never wait for the device.
+  std::vector<tb::ExcCount> exc_cache;
+  // pinned host scratch for small device->host reads (exchange counts: [nranks][nranks]);
+  // h_exc is the tensor-grid exception count's own word
   unsigned *h_counts = nullptr;
+  unsigned *h_exc = nullptr;
+  // host-buffer calls: chunks per call (0 = chosen from the bytes that cross PCIe)
+  int host_chunks = 0;
+  // multi-rank: state of the exchange in flight (one per context; comm.cu)
+  tb::ExchangeState *xs = nullptr;
+  int exchange_mode = 1;  // 1: peer-memory mailboxes where available, 0: NCCL all-to-all-v
 };
 
 struct tbslas_tree {
@@ -143,9 +169,17 @@ struct tbslas_tree {
   bool pt_count_valid = false;
   uint64_t struct_hash = 0;    // hash of (keys, depths): trees with equal hashes and leaf counts
                                // share their leaf list, so one locate/bin pass serves them all
+  uint64_t global_hash = 0;    // the same over the leaf lists of ALL ranks (sharded trees): decisions
+                               // every rank must take alike (one evaluation or one per tree) use it
+  bool boxes_all = false;      // boxes_ok on every rank that holds leaves of this tree
   bool boxes_ok = false;       // leaves are aligned, non-overlapping octants: "point inside the
                                // box of leaf j" implies "j is the last leaf with key <= key(point)"
   double *d_coeff = nullptr;   // [(n_leaf+1)*stride]; block n_leaf is all zero (null leaf)
+  // tbslas_b200_tree_update_coeff_async: the upload runs on the context's copy-in stream; the next
+  // reader (or writer) of d_coeff on the context's stream waits for ev_coeff first (tree_coeff_ready)
+  cudaEvent_t ev_coeff = nullptr;
+  bool coeff_pending = false;
+  size_t n_leaf_max = 0;       // most local leaves any rank holds (== n_leaf in a single-rank context)
   bool replicated = false;  // multi-rank context, but every rank holds the WHOLE tree: no exchange
   // Morton-range sharding (nranks > 1)
   long long leaf_offset = 0;                 // global index of local leaf 0
@@ -157,6 +191,7 @@ namespace tb {
 
 int fail(tbslas_ctx *ctx, int code, const char *fmt, ...);
 int ws_get(tbslas_ctx *ctx, Slot s, size_t bytes, void **out);
+int tree_coeff_ready(const tbslas_tree *t);  // orders the context's stream after a pending async upload
 
 struct StageScope {  // CUDA-event bracket of one stage on the context's stream
   tbslas_ctx *ctx;
@@ -191,6 +226,8 @@ struct LocateArgs {
   uint32_t *count;        // [n_leaf+2 (+kMaxRanks) +1] zeroed by the launcher; the last word is
                           // the evaluation kernel's chunk counter
   uint32_t *send_count;   // [nranks] (multi-rank only, zeroed by the launcher) or nullptr
+  const uint32_t *n_dev = nullptr;  // != nullptr: the point count lives on the device (<= n, which
+                                    // then only sizes the grid): points received through the mailbox
 };
 int launch_locate(tbslas_ctx *ctx, const LocateArgs &a);
 // scan of bin counts, tile map, scatter of point ids
@@ -212,6 +249,8 @@ struct BinArgs {
   int nranks = 1;
   double *send_pos = nullptr;            // [n_out][3]
   uint32_t *send_idx = nullptr;          // [n_out] origin index of each packed point
+  const PxPack *px = nullptr;            // peer exchange: coordinates go straight to the owners
+  const uint32_t *n_dev = nullptr;       // see LocateArgs
 };
 int launch_bin(tbslas_ctx *ctx, const BinArgs &a);
 
@@ -260,7 +299,7 @@ int set_pt2coeff(tbslas_ctx *ctx, int q, const double *M_host);
 int launch_refit(tbslas_ctx *ctx, tbslas_tree *t, const double *vals, int point_major);
 // tensor_eval.cu
 int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree *grid, size_t leaf0,
-                            size_t n_leaf, int bc, double *x, double *out, double alpha);
+                            size_t n_leaf, int bc, double *x, double *out, double alpha, bool gen_points);
 // tailnorm.cu
 int launch_tail_norm(tbslas_ctx *ctx, const tbslas_tree *t, double *out);
 // peak.cu

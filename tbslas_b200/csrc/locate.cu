@@ -51,9 +51,15 @@ template <bool MULTI, bool BOXES>
 __global__ void __launch_bounds__(kLocateThreads)
 locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes,
               const uint32_t *__restrict__ cells, int cell_shift, int n_leaf, int periodic,
-              double *__restrict__ pos, size_t n, int32_t *__restrict__ leaf_out,
+              double *__restrict__ pos, size_t n, const uint32_t *__restrict__ n_dev,
+              int32_t *__restrict__ leaf_out,
               uint32_t *__restrict__ rank_out, uint32_t *__restrict__ count,
               const uint64_t *__restrict__ splitters, int nranks, int myrank) {
+  if (n_dev) {  // point count known on the device only: the grid was sized for the capacity
+    const size_t nd = *n_dev;
+    n = nd < n ? nd : n;
+    if ((size_t)blockIdx.x * (kLocateThreads * kLocItems) >= n) return;
+  }
   __shared__ int s_bin[kLocTable];
   __shared__ unsigned s_cnt[kLocTable];
   __shared__ unsigned s_base[kLocTable];
@@ -272,7 +278,7 @@ int launch_locate(tbslas_ctx *ctx, const LocateArgs &a) {
 #define TB_LOCATE(M, B)                                                                          \
   locate_kernel<M, B><<<grid, kLocateThreads, 0, ctx->stream>>>(                                 \
       t->d_key, t->d_box, t->d_cell, t->cell_shift, (int)t->n_leaf, a.periodic, a.pos, a.n,      \
-      a.leaf, a.rank, a.count,                                                                   \
+      a.n_dev, a.leaf, a.rank, a.count,                                                                   \
       multi ? t->d_splitters : nullptr, multi ? ctx->nranks : 1, multi ? ctx->rank : 0)
   if (multi) {
     if (boxes) TB_LOCATE(true, true); else TB_LOCATE(true, false);
@@ -368,18 +374,22 @@ __global__ void tile_map_kernel(const uint32_t *__restrict__ bin_start,
   tile_map[t] = make_int2(lo, (int)(__ldg(bin_start + lo) + (t - __ldg(tile_start + lo)) * tile_pts));
 }
 
-// Insiders: point id -> its slot in the leaf grouping.  Outsiders (MULTI): coordinates and
-// origin index -> the send bucket of the owner rank (reference: the forward scatter of
-// par::ScatterForward, tree_functor.h:574-575); bucket offsets = exclusive scan of the
-// per-rank send counts, rebuilt per CTA in shared memory (nranks <= 64).
-template <bool MULTI>
+// Insiders: point id -> its slot in the leaf grouping.  Outsiders: coordinates and origin index
+// -> the bucket of the owner rank (reference: the forward scatter of par::ScatterForward,
+// tree_functor.h:574-575).  MODE 1 (NCCL exchange): a local send buffer in bucket order, bucket
+// offsets = exclusive scan of the per-rank send counts, rebuilt per CTA in shared memory
+// (nranks <= 64).  MODE 2 (peer exchange): the coordinates go straight into the owner's receive
+// buffer over NVLink peer memory, at the place comm.cu's px_offsets_kernel derived from the count
+// matrix; only the origin index stays here (bucket order, for the unpack).
+template <int MODE>
 __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint32_t *__restrict__ rank,
                                     const uint32_t *__restrict__ bin_start, size_t n,
+                                    const uint32_t *__restrict__ n_dev,
                                     uint32_t *__restrict__ perm, const double *__restrict__ pos,
                                     const uint32_t *__restrict__ send_count, int nranks,
-                                    double *__restrict__ send_pos, uint32_t *__restrict__ send_idx) {
-  __shared__ unsigned s_off[kMaxRanks];
-  if (MULTI) {
+                                    double *__restrict__ send_pos, uint32_t *__restrict__ send_idx, PxPack px) {
+  __shared__ unsigned s_off[kMaxRanks], s_dst[kMaxRanks];
+  if (MODE == 1) {
     if (threadIdx.x == 0) {
       unsigned run = 0;
       for (int r = 0; r < nranks; r++) {
@@ -389,17 +399,36 @@ __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint
     }
     __syncthreads();
   }
+  if (MODE == 2) {
+    if ((int)threadIdx.x < nranks) {
+      s_off[threadIdx.x] = px.send_off[threadIdx.x];
+      s_dst[threadIdx.x] = px.dst_off[threadIdx.x];
+    }
+    __syncthreads();
+  }
+  if (n_dev) {
+    const size_t nd = *n_dev;
+    n = nd < n ? nd : n;
+  }
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int j = leaf[i];
   if (j >= 0) {
     perm[__ldg(bin_start + j) + rank[i]] = (uint32_t)i;
-  } else if (MULTI) {  // travels to its owner
+  } else if (MODE == 1) {  // travels to its owner
     const unsigned slot = s_off[-2 - j] + rank[i];
     send_pos[3 * (size_t)slot] = pos[3 * i];
     send_pos[3 * (size_t)slot + 1] = pos[3 * i + 1];
     send_pos[3 * (size_t)slot + 2] = pos[3 * i + 2];
     send_idx[slot] = (uint32_t)i;
+  } else if (MODE == 2) {
+    const int o = -2 - j;
+    const unsigned r = rank[i];
+    double *dst = reinterpret_cast<double *>(px.peer_base[o] + px.off_recv_pos) + 3 * ((size_t)s_dst[o] + r);
+    dst[0] = pos[3 * i];
+    dst[1] = pos[3 * i + 1];
+    dst[2] = pos[3 * i + 2];
+    send_idx[s_off[o] + r] = (uint32_t)i;
   }
 }
 
@@ -416,13 +445,17 @@ int launch_bin(tbslas_ctx *ctx, const BinArgs &a) {
   }
   if (a.n) {
     const unsigned grid = (unsigned)((a.n + 255) / 256);
-    if (a.send_count)
-      scatter_perm_kernel<true><<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.perm,
-                                                             a.pos, a.send_count, a.nranks,
-                                                             a.send_pos, a.send_idx);
+    if (a.px)
+      scatter_perm_kernel<2><<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.n_dev, a.perm,
+                                                          a.pos, a.send_count, a.nranks, nullptr, a.send_idx,
+                                                          *a.px);
+    else if (a.send_count)
+      scatter_perm_kernel<1><<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.n_dev, a.perm,
+                                                          a.pos, a.send_count, a.nranks, a.send_pos, a.send_idx,
+                                                          PxPack());
     else
-      scatter_perm_kernel<false><<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.perm,
-                                                              nullptr, nullptr, 1, nullptr, nullptr);
+      scatter_perm_kernel<0><<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.n_dev, a.perm,
+                                                          nullptr, nullptr, 1, nullptr, nullptr, PxPack());
     TB_CUDA(ctx, cudaGetLastError());
   }
   return TBSLAS_OK;

@@ -79,6 +79,8 @@ struct TensorParams {
   size_t n_leaf;
   int d, periodic;
   const double *x;          // [n_leaf * P][3] the grid points
+  double *xgen;             // != nullptr: the grid points are WRITTEN here first (== x): the kernel is
+                            // also tbslas::CollectChebTreeGridPoints (gridpts.cu) for these leaves
   double *out;              // [n_leaf * P][3] = x + alpha * v on regular points
   double alpha;
   unsigned *exc_count;      // exceptions: number and point ids
@@ -100,6 +102,17 @@ tensor_grid_eval_kernel(const TensorParams p, const TensorTables tb_) {
     const int j = p.map[leaf];
     const size_t gp0 = leaf * (size_t)P;
     __syncthreads();  // previous leaf done with the shared arrays
+    if (p.xgen) {  // arrival points of this leaf, formed exactly as gridpts.cu forms them
+      const double4 gc = p.ggeom[leaf];
+      const double glen = 1.0 / (double)(1u << p.gdepth[leaf]);
+      double *o = p.xgen + 3 * gp0;
+      for (int e = t; e < 3 * P; e += kTensorThreads) {
+        const int pt = e / 3, a = e - 3 * pt;
+        const int pz = pt / (d * d), rem = pt - pz * d * d, py = rem / d, px = rem - py * d;
+        const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z);
+        o[e] = __dadd_rn(c, __dmul_rn(glen, tb_.node[a == 0 ? px : (a == 1 ? py : pz)]));
+      }
+    }
     if (t < 3) s_ok[t] = 0u;
     if (t == 0) s_exc_n = 0u;
     __syncthreads();
@@ -212,6 +225,17 @@ tensor_grid_eval_kernel_t(const TensorParams p, const TensorTables tb_) {
     const int j = p.map[leaf];
     const size_t gp0 = leaf * (size_t)P;
     __syncthreads();
+    if (p.xgen) {  // arrival points of this leaf, formed exactly as gridpts.cu forms them
+      const double4 gc = p.ggeom[leaf];
+      const double glen = 1.0 / (double)(1u << p.gdepth[leaf]);
+      double *o = p.xgen + 3 * gp0;
+      for (int e = t; e < 3 * P; e += kTensorThreads) {
+        const int pt = e / 3, a = e - 3 * pt;
+        const int pz = pt / (D * D), rem = pt - pz * D * D, py = rem / D, px = rem - py * D;
+        const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z);
+        o[e] = __dadd_rn(c, __dmul_rn(glen, tb_.node[a == 0 ? px : (a == 1 ? py : pz)]));
+      }
+    }
     if (t < 3) s_ok[t] = 0u;
     if (t == 0) s_exc_n = 0u;
     if (j >= 0) {  // in flight while the bases are built
@@ -363,36 +387,43 @@ __global__ void scatter_update_kernel(const double *__restrict__ pos, const doub
 }
 
 // Stage 1 of the first RK2 sub-step on the grid points of leaves [leaf0, leaf0 + n_leaf) of `grid`:
-// out = x + alpha * vel(x).  `x` is rewritten only where the periodic wrap changes it.
-// Returns TBSLAS_ERR_UNSUPPORTED (without touching anything) when the shortcut does not apply.
+// out = x + alpha * vel(x).  `x` is rewritten only where the periodic wrap changes it -- or, with
+// gen_points, WRITTEN: the kernel then also produces the arrival points (gridpts.cu's job).
+// Returns TBSLAS_ERR_UNSUPPORTED (without touching anything) when the shortcut does not apply; in a
+// multi-rank context that decision only uses what every rank knows, because the generic pass over the
+// exceptions of a Morton-sharded velocity tree is a collective evaluation.
 int eval_tree_dev_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out);  // api.cu
 
 int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree *grid, size_t leaf0,
-                            size_t n_leaf, int bc, double *x, double *out, double alpha) {
-  if (vel->dof != 3 || vel->q != grid->q || !vel->boxes_ok || !grid->boxes_ok || !vel->n_leaf ||
-      (ctx->nranks > 1 && !vel->replicated))
+                            size_t n_leaf, int bc, double *x, double *out, double alpha, bool gen_points) {
+  const bool collective = ctx->nranks > 1 && !vel->replicated;
+  if (vel->dof != 3 || vel->q != grid->q || !vel->boxes_all || !grid->boxes_all || (!collective && !vel->n_leaf))
     return TBSLAS_ERR_UNSUPPORTED;
   const int d = vel->q + 1, dp = d | 1, P = d * d * d, n_row = d * (d + 1) / 2;
   const size_t n = n_leaf * (size_t)P;
-  if (!n) return TBSLAS_OK;
+  if (!n && !collective) return TBSLAS_OK;
   if (n >= (size_t)0xfffffff0u) return TBSLAS_ERR_UNSUPPORTED;
-  TensorTables tt;
-  new_nodes_host(vel->q, tt.node);
-  int off = 0, r = 0;
-  for (int i = 0; i < d; i++) {
-    tt.row_first[i] = (uint16_t)r;
-    for (int j = 0; i + j < d; j++) {
-      tt.row_off[r++] = (uint16_t)off;
-      off += d - i - j;
+  TB_TRY(tree_coeff_ready(vel));
+  const int periodic = (bc == TBSLAS_PERIODIC);
+  void *exc_idx = nullptr, *misc = nullptr;
+  unsigned *exc_count = nullptr;
+  if (n) {
+    TensorTables tt;
+    new_nodes_host(vel->q, tt.node);
+    int off = 0, r = 0;
+    for (int i = 0; i < d; i++) {
+      tt.row_first[i] = (uint16_t)r;
+      for (int j = 0; i + j < d; j++) {
+        tt.row_off[r++] = (uint16_t)off;
+        off += d - i - j;
+      }
     }
-  }
-  tt.row_first[d] = (uint16_t)r;
-  void *map, *exc_idx, *misc;
-  TB_TRY(ws_get(ctx, WS_GRIDMAP, sizeof(int32_t) * n_leaf, &map));
-  TB_TRY(ws_get(ctx, WS_EXC_IDX, sizeof(uint32_t) * (n + 1), &exc_idx));
-  TB_TRY(ws_get(ctx, WS_MISC, 64, &misc));
-  unsigned *exc_count = (unsigned *)misc;
-  {
+    tt.row_first[d] = (uint16_t)r;
+    void *map;
+    TB_TRY(ws_get(ctx, WS_GRIDMAP, sizeof(int32_t) * n_leaf, &map));
+    TB_TRY(ws_get(ctx, WS_EXC_IDX, sizeof(uint32_t) * (n + 1), &exc_idx));
+    TB_TRY(ws_get(ctx, WS_MISC, 64, &misc));
+    exc_count = (unsigned *)misc;
     StageScope sc(ctx, ST_TENSOR, (double)n, 2);
     TB_CUDA(ctx, cudaMemsetAsync(exc_count, 0, sizeof(unsigned), ctx->stream));
     grid_leaf_map_kernel<<<(unsigned)((n_leaf + 255) / 256), 256, 0, ctx->stream>>>(
@@ -410,8 +441,9 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
     p.map = (const int32_t *)map;
     p.n_leaf = n_leaf;
     p.d = d;
-    p.periodic = (bc == TBSLAS_PERIODIC);
+    p.periodic = periodic;
     p.x = x;
+    p.xgen = gen_points ? x : nullptr;
     p.out = out;
     p.alpha = alpha;
     p.exc_count = exc_count;
@@ -434,34 +466,53 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
       }
     }
   }
-  // The exceptions go through the generic path: one host-visible count per call.  A kernel stores it
-  // into the (device-accessible) pinned word: a cudaMemcpy would queue on the device-to-host copy
-  // engine behind the previous chunk's values (hundreds of MB in the pipelined host calls) and stall
-  // this stream for as long as that copy takes.
-  publish_count_kernel<<<1, 1, 0, ctx->stream>>>(exc_count, ctx->h_counts);
-  TB_CUDA(ctx, cudaGetLastError());
-  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const size_t m = ctx->h_counts[0];
+  // The exceptions go through the generic path, whose launches the host sizes: it needs their number.
+  // Which arrival points are exceptions is decided by the two leaf lists and the boundary condition
+  // alone (integer boxes and node positions; no coefficient enters), so the count is read back from
+  // the device ONCE per (grid leaf range, velocity tree, bc) and remembered: a step on unchanged trees
+  // never waits for the device.  The first time, a kernel stores the count into a device-accessible
+  // pinned word (a cudaMemcpy would queue on the device-to-host copy engine behind the previous
+  // chunk's values in the pipelined host calls).
+  size_t m = 0;
+  if (n) {
+    ExcCount key{vel->struct_hash, grid->struct_hash, vel->n_leaf, grid->n_leaf, leaf0, n_leaf, vel->q, periodic, 0};
+    ExcCount *hit = nullptr;
+    for (ExcCount &e : ctx->exc_cache)
+      if (e.vel_hash == key.vel_hash && e.grid_hash == key.grid_hash && e.vel_leaves == key.vel_leaves &&
+          e.grid_leaves == key.grid_leaves && e.leaf0 == key.leaf0 && e.n_leaf == key.n_leaf && e.q == key.q &&
+          e.periodic == key.periodic)
+        hit = &e;
+    if (hit) {
+      m = hit->count;
+    } else {
+      publish_count_kernel<<<1, 1, 0, ctx->stream>>>(exc_count, ctx->h_exc);
+      TB_CUDA(ctx, cudaGetLastError());
+      TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      m = key.count = ctx->h_exc[0];
+      if (ctx->exc_cache.size() >= 256) ctx->exc_cache.erase(ctx->exc_cache.begin());
+      ctx->exc_cache.push_back(key);
+    }
+  }
   ctx->last_exceptions = m;
-  if (!m) return TBSLAS_OK;
+  if (!m && !collective) return TBSLAS_OK;
   void *epos, *eval;
-  // sized with headroom: the count differs a little from call to call and a growing workspace
-  // slot is a cudaFree + cudaMalloc
+  // sized with headroom: the count differs from chunk to chunk and a growing workspace slot is a
+  // cudaFree + cudaMalloc
   const size_t cap = m > n / 8 + 4096 ? m + m / 4 : n / 8 + 4096;
   TB_TRY(ws_get(ctx, WS_EXC_POS, sizeof(double) * 3 * cap, &epos));
   TB_TRY(ws_get(ctx, WS_EXC_VAL, sizeof(double) * 3 * cap, &eval));
   const unsigned g3 = (unsigned)((3 * m + 255) / 256);
-  {
+  if (m) {
     StageScope sc(ctx, ST_TENSOR, 0.0, 1);
     gather_points_kernel<<<g3, 256, 0, ctx->stream>>>(x, (const uint32_t *)exc_idx, m, (double *)epos);
     TB_CUDA(ctx, cudaGetLastError());
   }
   TB_TRY(eval_tree_dev_points(vel, bc, (double *)epos, m, (double *)eval));
-  {
+  if (m) {
     StageScope sc(ctx, ST_TENSOR, 0.0, 1);
     scatter_update_kernel<<<g3, 256, 0, ctx->stream>>>((const double *)epos, (const double *)eval,
                                                        (const uint32_t *)exc_idx, m, alpha,
-                                                       bc == TBSLAS_PERIODIC, x, out);
+                                                       periodic, x, out);
     TB_CUDA(ctx, cudaGetLastError());
   }
   return TBSLAS_OK;
