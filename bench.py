@@ -390,7 +390,7 @@ def run_b200(args):
         n_s = min(args.parity_points, n_local)
         e_dep = e_val = e_step = 0.0
         if n_s:
-            idx = torch.linspace(0, n_local - 1, n_s, device=dev).long()
+            idx = torch.arange(n_s, device=dev, dtype=torch.int64) * (n_local // n_s)
             arr, dep_g, got = pos[idx].cpu().numpy(), pdep[idx].cpu().numpy(), pv[idx].cpu().numpy()
             hv = [orc.tree_create(v) for v in wl.vel]
             hc = orc.tree_create(wl.con)

@@ -472,28 +472,53 @@ struct PipeSpec {
 enum { EV_IN = 0, EV_A, EV_POSOUT, EV_B, EV_OUT };
 
 // Chunks of a host-buffer call.  What is exposed is the copy-in of the first chunk (calls with host
-// input) and the copy-out of the last one, so chunks should be small; what a chunk costs is a few
-// launches' worth of ramp-up and tail of the persistent kernels, so not too small: about 16 Mi
-// points (128 MB of values, ~2.5 ms of PCIe) per chunk for tree-level calls, 4 Mi with host input,
-// never more than 16 chunks.  `n_collective`: in a multi-rank context every chunk is a collective
-// evaluation, so the count must be the same on every rank: it is derived from a size all ranks
-// know (the largest shard's arrival points for tree-level calls) or is the fixed 8.
+// input) and the copy-out of the last one; what a chunk costs is the ramp-up and tail of every
+// kernel it launches (measured on C2: about 1 ms per chunk, profiles/r02_e2e_chunk_sweep.json).
+//  * calls with host input are bound by the copy-in: uniform chunks of about 4 Mi points, <= 16;
+//  * tree-level calls (arrival points generated in HBM, only values leave) use chunks of
+//    geometrically DEcreasing size -- 1/2, 1/4, ... of the leaves, the last two equal, the last about
+//    8 Mi points (64 MB, ~1.2 ms of PCIe): the copy-out of chunk c (40 ms per 2.2 GB) always fits under
+//    the kernels of chunk c+1 (89 ms per 274 M points at half the size), so only the last, small copy is
+//    exposed and log2(n / 8 Mi) + 1 chunks do what 32 uniform ones would.
+// `n_collective`: in a multi-rank context every chunk is a collective evaluation, so the count must be
+// the same on every rank: it is derived from a size all ranks know (the largest shard's arrival points
+// for tree-level calls) or is the fixed 8.
 static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input, size_t n_collective) {
   if (ctx->host_chunks > 0) return ctx->host_chunks;
   if (ctx->nranks > 1) {
     if (!n_collective) return 8;
     n = n_collective;
   }
-  const size_t per = has_input ? ((size_t)4 << 20) : ((size_t)16 << 20);
-  const size_t k = (n + per / 2) / per;
-  return (int)(k < 1 ? 1 : (k > 16 ? 16 : k));
+  if (has_input) {
+    const size_t per = (size_t)4 << 20, k = (n + per / 2) / per;
+    return (int)(k < 1 ? 1 : (k > 16 ? 16 : k));
+  }
+  int k = 1;
+  for (size_t m = n; m >= ((size_t)16 << 20) && k < 12; m >>= 1) k++;
+  return k;
+}
+
+// first unit of chunk c of K over U units: uniform, or halving (1/2, 1/4, ..., the last two equal)
+static size_t chunk_first_unit(size_t U, int K, int c, bool halving) {
+  if (c <= 0) return 0;
+  if (c >= K) return U;
+  if (!halving || K < 3) return (size_t)(((unsigned __int128)U * (unsigned)c) / (unsigned)K);
+  // sum_{i<c} 2^-(i+1) = 1 - 2^-c
+  return U - (U >> c);
 }
 
 template <class FA, class FB>
 static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA phase_a, FB phase_b) {
-  const int K = pipe_chunks(ctx, n, sp.h_pos != nullptr, sp.n_collective);
+  const bool has_input = sp.h_pos != nullptr;
+  const int K = pipe_chunks(ctx, n, has_input, sp.n_collective);
   const size_t unit = sp.unit ? sp.unit : 1;
-  const size_t chunk = ((n / unit + K - 1) / K) * unit + (n % unit ? unit : 0);
+  const size_t U = (n + unit - 1) / unit;
+  const bool halving = !has_input && ctx->host_chunks == 0;
+  size_t chunk = 0;  // largest chunk, in points
+  for (int c = 0; c < K; c++) {
+    const size_t u = chunk_first_unit(U, K, c + 1, halving) - chunk_first_unit(U, K, c, halving);
+    if (u * unit > chunk) chunk = u * unit;
+  }
   PipeBufs bufs[2] = {};
   const Slot pos_slot[2] = {WS_POS_A, WS_POS_C}, val_slot[2] = {WS_VAL_B, WS_VAL_C},
              leaf_slot[2] = {WS_LEAFOUT, WS_LEAFOUT2};
@@ -515,20 +540,28 @@ static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA p
   TB_CUDA(ctx, cudaEventRecord(ev(EV_B, 1), s_run));
   for (int c = 0; c < K; c++) {
     const int b = c & 1;
-    const size_t off = (size_t)c * chunk;
-    const size_t m = off < n ? (n - off < chunk ? n - off : chunk) : 0;
+    size_t off = chunk_first_unit(U, K, c, halving) * unit, end = chunk_first_unit(U, K, c + 1, halving) * unit;
+    if (off > n) off = n;
+    if (end > n) end = n;
+    const size_t m = end - off;
     PipeBufs &B = bufs[b];
-    // ---- copy in (buffer b is free once chunk c-2 has been computed and copied out)
-    TB_CUDA(ctx, cudaStreamWaitEvent(s_in, ev(EV_B, b), 0));
-    TB_CUDA(ctx, cudaStreamWaitEvent(s_in, ev(EV_OUT, b), 0));
-    if (m && sp.h_pos) {
-      TB_CUDA(ctx, cudaMemcpyAsync(B.pos, sp.h_pos + 3 * off, sizeof(double) * 3 * m,
-                                   cudaMemcpyHostToDevice, s_in));
-      ctx->acc_units[ST_H2D] += (double)(24 * m);
+    if (has_input) {
+      // ---- copy in (buffer b is free once chunk c-2 has been computed and copied out)
+      TB_CUDA(ctx, cudaStreamWaitEvent(s_in, ev(EV_B, b), 0));
+      TB_CUDA(ctx, cudaStreamWaitEvent(s_in, ev(EV_OUT, b), 0));
+      if (m) {
+        TB_CUDA(ctx, cudaMemcpyAsync(B.pos, sp.h_pos + 3 * off, sizeof(double) * 3 * m,
+                                     cudaMemcpyHostToDevice, s_in));
+        ctx->acc_units[ST_H2D] += (double)(24 * m);
+      }
+      TB_CUDA(ctx, cudaEventRecord(ev(EV_IN, b), s_in));
+      TB_CUDA(ctx, cudaStreamWaitEvent(s_run, ev(EV_IN, b), 0));
+    } else {
+      // nothing to copy in: the copy-in stream stays out of it (an asynchronous coefficient upload may
+      // be running there); buffer b is free once chunk c-2 has been copied out
+      TB_CUDA(ctx, cudaStreamWaitEvent(s_run, ev(EV_OUT, b), 0));
     }
-    TB_CUDA(ctx, cudaEventRecord(ev(EV_IN, b), s_in));
     // ---- compute
-    TB_CUDA(ctx, cudaStreamWaitEvent(s_run, ev(EV_IN, b), 0));
     TB_TRY(phase_a(B, m, off));
     if (sp.h_pos_a) {
       TB_CUDA(ctx, cudaEventRecord(ev(EV_A, b), s_run));
@@ -588,7 +621,8 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
   }
   ctx->stream = ctx->own_stream;
   bool ok = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
+            cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_aux, cudaStreamNonBlocking) == cudaSuccess;
   for (auto &pair : ctx->ev_pipe)
     for (cudaEvent_t &e : pair) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
   // device-writable pinned words: the exchange's count matrix (comm.cu) and, separately, the
@@ -628,6 +662,7 @@ int tbslas_b200_finalize(tbslas_ctx *ctx) {
       if (e) cudaEventDestroy(e);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  if (ctx->copy_aux) cudaStreamDestroy(ctx->copy_aux);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return TBSLAS_OK;
@@ -837,10 +872,10 @@ int tbslas_b200_tree_update_coeff_async(tbslas_tree *t, const double *coeff, int
   if (!t->ev_coeff) TB_CUDA(ctx, cudaEventCreateWithFlags(&t->ev_coeff, cudaEventDisableTiming));
   // readers of the old coefficients already enqueued on the context's stream finish first
   TB_CUDA(ctx, cudaEventRecord(t->ev_coeff, ctx->stream));
-  TB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, t->ev_coeff, 0));
+  TB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_aux, t->ev_coeff, 0));
   ctx->acc_units[ST_H2D] += (double)(t->n_leaf * t->dof * t->ncoef * 8);
-  TB_TRY(copy_coeff_in(t, coeff, mem, ctx->copy_in));
-  TB_CUDA(ctx, cudaEventRecord(t->ev_coeff, ctx->copy_in));
+  TB_TRY(copy_coeff_in(t, coeff, mem, ctx->copy_aux));
+  TB_CUDA(ctx, cudaEventRecord(t->ev_coeff, ctx->copy_aux));
   t->coeff_pending = true;
   return TBSLAS_OK;
 }
@@ -866,7 +901,7 @@ int tbslas_b200_tree_get_coeff(tbslas_tree *t, double *coeff, int mem) {
 int tbslas_b200_tree_destroy(tbslas_tree *t) {
   if (!t) return TBSLAS_ERR_INVALID;
   cudaStreamSynchronize(t->ctx->stream);
-  if (t->coeff_pending) cudaStreamSynchronize(t->ctx->copy_in);
+  if (t->coeff_pending) cudaStreamSynchronize(t->ctx->copy_aux);
   if (t->ev_coeff) cudaEventDestroy(t->ev_coeff);
   cudaFree(t->d_key);
   cudaFree(t->d_geom);

@@ -79,14 +79,18 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
     s_cend = 0;
   }
   __syncwarp();
-  // lane 0 writes the descriptor of the next tile of the stream into ring slot n % 3
+  // the descriptor of the next tile of the stream goes into ring slot n % 3 (written by lane 0)
   auto describe_next = [&](unsigned n) {
+    const unsigned n_tiles = __ldg(p.tile_start + p.n_bins);
+    // lane 0 decides whether a new chunk is due and takes it; the whole warp then finds the chunk's
+    // first leaf TOGETHER: a 32-ary search over tile_start (lane i probes the i-th of 32 evenly spaced
+    // bins, one ballot per round) needs ceil(log32(n_bins)) dependent loads -- 4 for 81 k leaves --
+    // where a one-lane binary search needs 17, with the other 31 lanes waiting for it.
+    unsigned t = 0;
+    int take = 0;  // 0: next tile of the current chunk, 1: new chunk at tile t, 2: end of stream
     if (lane == 0) {
-      const unsigned n_tiles = __ldg(p.tile_start + p.n_bins);
-      unsigned t = (unsigned)s_ctl[CT_NEXT];
-      int *r = s_ctl + CT_RING + 3 * (n % 3);
-      bool have = true;
-      if (t >= (unsigned)s_cend) {  // take the next chunk
+      t = (unsigned)s_ctl[CT_NEXT];
+      if (t >= (unsigned)s_cend) {
         // guided self-scheduling: a share of what is left, so the chunks shrink towards the
         // end of the launch and the workers finish within a couple of tiles of each other
         const unsigned done = *reinterpret_cast<volatile unsigned *>(chunk_counter);
@@ -95,28 +99,40 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
         sz = sz < 2u ? 2u : (sz > chunk ? chunk : sz);
         t = atomicAdd(chunk_counter, sz);
         if (t >= n_tiles) {
-          have = false;
+          take = 2;
           s_ctl[CT_NEXT] = (int)n_tiles;
           s_cend = (int)n_tiles;
         } else {
+          take = 1;
           s_cend = (int)min(t + sz, n_tiles);
-          // leaf of tile t = last bin j with tile_start[j] <= t
-          int lo = 0, hi = p.n_bins;
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(p.tile_start + mid) <= t)
-              lo = mid;
-            else
-              hi = mid;
-          }
-          s_ctl[CT_WL] = lo;
-          s_ctl[CT_TS] = (int)__ldg(p.tile_start + lo);
-          s_ctl[CT_TE] = (int)__ldg(p.tile_start + lo + 1);
-          s_ctl[CT_BS] = (int)__ldg(p.bin_start + lo);
-          s_ctl[CT_BE] = (int)__ldg(p.bin_start + lo + 1);
         }
       }
-      if (have) {
+    }
+    take = __shfl_sync(0xffffffffu, take, 0);
+    if (take == 1) {
+      t = __shfl_sync(0xffffffffu, t, 0);
+      // leaf of tile t = last bin j with tile_start[j] <= t  (tile_start[n_bins] = n_tiles > t)
+      int lo = 0, hi = p.n_bins;
+      while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        const int pos = lo + (lane + 1) * step;
+        const bool le = pos < hi && __ldg(p.tile_start + pos) <= t;  // true on a prefix of the lanes
+        const int cnt = __popc(__ballot_sync(0xffffffffu, le));
+        const int nlo = lo + cnt * step;
+        hi = min(nlo + step, hi);
+        lo = nlo;
+      }
+      if (lane == 0) {
+        s_ctl[CT_WL] = lo;
+        s_ctl[CT_TS] = (int)__ldg(p.tile_start + lo);
+        s_ctl[CT_TE] = (int)__ldg(p.tile_start + lo + 1);
+        s_ctl[CT_BS] = (int)__ldg(p.bin_start + lo);
+        s_ctl[CT_BE] = (int)__ldg(p.bin_start + lo + 1);
+      }
+    }
+    if (lane == 0) {
+      int *r = s_ctl + CT_RING + 3 * (n % 3);
+      if (take != 2) {
         int wl = s_ctl[CT_WL];
         unsigned ts = (unsigned)s_ctl[CT_TS], te = (unsigned)s_ctl[CT_TE];
         unsigned bs = (unsigned)s_ctl[CT_BS], be = (unsigned)s_ctl[CT_BE];

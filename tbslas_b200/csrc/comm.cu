@@ -460,7 +460,7 @@ int px_setup(tbslas_ctx *ctx, size_t cap) {
   static_assert(sizeof(Msg) <= 128, "message");
   memset(&mine, 0, sizeof(mine));
   bool ok = !disabled && cap > 0 && cudaMalloc(&x.mailbox, x.lay.bytes()) == cudaSuccess;
-  if (ok) ok = cudaMemset(x.mailbox, 0, kPxHeaderBytes) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(x.mailbox, 0, kPxHeaderBytes, ctx->stream) == cudaSuccess;  // ordered before the handle leaves
   if (ok) ok = cudaIpcGetMemHandle(&mine.h, x.mailbox) == cudaSuccess;
   if (ok && !x.d_peers) ok = cudaMalloc(&x.d_peers, sizeof(PxPeers)) == cudaSuccess;
   if (ok && !x.d_info) ok = cudaMalloc(&x.d_info, sizeof(PxInfo)) == cudaSuccess;

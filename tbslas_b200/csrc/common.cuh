@@ -125,6 +125,7 @@ struct tbslas_ctx {
   size_t last_sent = 0, last_recv = 0;  // outsiders of the most recent tree evaluation
   // host-buffer calls: H2D / compute / D2H of consecutive chunks overlap on three streams
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaStream_t copy_aux = nullptr;  // asynchronous coefficient uploads
   cudaEvent_t ev_pipe[5][2] = {};  // [in, phaseA, pos_out, phaseB, out][buffer parity]
   tb::Pt2Coeff pt2coeff[TBSLAS_MAX_CHEB_DEG + 1];
   // FieldSetFunctor / FieldExtrapFunctor over trees with one leaf list: 1 = combine the trees'
