@@ -528,6 +528,13 @@ def run_b200(args):
     for _ in range(2):
         step_tree()
     barrier()
+    # raw PCIe rate of this rank's values, all ranks copying at once (what bounds the copy-out)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    h_vals.copy_(vals, non_blocking=True)
+    c1.record()
+    barrier()
+    d2h_gbps = -allmax(-(n_local * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9)) if n_local else 0.0
     e2e_steps = args.steps
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -626,7 +633,8 @@ def run_b200(args):
         # (SolveSemilagInSitu, advection.cpp:296) through the C ABI with pinned HOST buffers
         "e2e": {"value": n_total / tree_s, "unit": "points/s", "ms_per_step": tree_s * 1e3,
                 "h2d_bytes_per_step": int(con_local.n_leaf * nc * 8), "d2h_bytes_per_step": int(n_local * 8),
-                "steps": e2e_steps, "checksum": checksum_tree, "checksum_bits": h_bits,
+                "steps": e2e_steps, "pcie_d2h_GBps_slowest_rank": d2h_gbps,
+                "checksum": checksum_tree, "checksum_bits": h_bits,
                 "bit_identical_to_device_buffers": bool(h_bits == checksum_bits),
                 "what": "tbslas_b200_tree_update_coeff_async + tbslas_b200_semilag_insitu (SolveSemilagInSitu "
                         "steps 1-2, tree_semilag.h:92-130): the advected tree's coefficients up from pinned "

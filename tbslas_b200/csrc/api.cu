@@ -1,6 +1,7 @@
 // C ABI of libtbslas_b200.so: context, trees and the host-side orchestration of the
 // semi-Lagrangian hot path (see include/tbslas_b200.h for the contract and the
 // reference file:line each entry point replaces).
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -370,7 +371,7 @@ static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos,
 static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, double *xsol,
                         double *xtmp, size_t n, double tinit, double tfinal, int nrk,
                         const double *x0 = nullptr, const tbslas_tree *grid = nullptr, size_t leaf0 = 0,
-                        bool gen_points = false) {
+                        bool gen_points = false, size_t n_call = 0) {
   const double tau = (tfinal - tinit) / nrk;  // traj.inc:55
   double tcur = tinit;
   tbslas_ctx *ctx = f1->tree[0]->ctx;
@@ -388,7 +389,9 @@ static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, 
       // small point sets are latency bound either way; a Morton-sharded velocity tree makes the
       // shortcut's generic pass a collective, so there the choice must not depend on this rank's n
       const bool sharded = ctx->nranks > 1 && !f1->tree[0]->replicated;
-      if (ctx->tensor_grid && (n >= ctx->tensor_grid_min_points || sharded) && n % P == 0) {
+      // (`n_call`: points of the whole call when this is one chunk of it -- every chunk takes the path
+      // the un-chunked call would, so the chunked host flavour returns the same bits)
+      if (ctx->tensor_grid && ((n_call ? n_call : n) >= ctx->tensor_grid_min_points || sharded) && n % P == 0) {
         tbslas_tree view, *one = nullptr;
         TB_TRY(field_single_tree(ctx, f1, tcur, &view, &one));
         if (one) {
@@ -476,13 +479,19 @@ enum { EV_IN = 0, EV_A, EV_POSOUT, EV_B, EV_OUT };
 // kernel it launches (measured on C2: about 1 ms per chunk, profiles/r02_e2e_chunk_sweep.json).
 //  * calls with host input are bound by the copy-in: uniform chunks of about 4 Mi points, <= 16;
 //  * tree-level calls (arrival points generated in HBM, only values leave) use chunks of
-//    geometrically DEcreasing size -- 1/2, 1/4, ... of the leaves, the last two equal, the last about
-//    8 Mi points (64 MB, ~1.2 ms of PCIe): the copy-out of chunk c (40 ms per 2.2 GB) always fits under
-//    the kernels of chunk c+1 (89 ms per 274 M points at half the size), so only the last, small copy is
-//    exposed and log2(n / 8 Mi) + 1 chunks do what 32 uniform ones would.
+//    geometrically DEcreasing size, ratio kChunkRatio.  The copy-out of chunk c then runs under the
+//    kernels of chunk c+1, which is kChunkRatio times as large: that fits as long as copying a point's
+//    values out takes less than kChunkRatio of computing it -- 8 B at ~50 GB/s = 0.16 ns against
+//    0.32 ns per point of the q = 8..14 step, i.e. 0.5 (measured, also with every GPU of the box
+//    copying at once: 47 GB/s) -- so only the last, small copy is exposed and about log(n / 8 Mi)
+//    chunks do what dozens of uniform ones would.
 // `n_collective`: in a multi-rank context every chunk is a collective evaluation, so the count must be
 // the same on every rank: it is derived from a size all ranks know (the largest shard's arrival points
 // for tree-level calls) or is the fixed 8.
+constexpr double kChunkRatio = 0.62;
+static double chunk_cum(int K, int c) {  // fraction of the units in chunks 0..c-1
+  return (1.0 - pow(kChunkRatio, c)) / (1.0 - pow(kChunkRatio, K));
+}
 static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input, size_t n_collective) {
   if (ctx->host_chunks > 0) return ctx->host_chunks;
   if (ctx->nranks > 1) {
@@ -493,18 +502,18 @@ static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input, size_t n_colle
     const size_t per = (size_t)4 << 20, k = (n + per / 2) / per;
     return (int)(k < 1 ? 1 : (k > 16 ? 16 : k));
   }
-  int k = 1;
-  for (size_t m = n; m >= ((size_t)16 << 20) && k < 12; m >>= 1) k++;
+  int k = 1;  // fewest chunks whose last one holds at most 8 Mi points
+  while (k < 12 && (double)n * (1.0 - chunk_cum(k, k - 1)) > (double)((size_t)8 << 20)) k++;
   return k;
 }
 
-// first unit of chunk c of K over U units: uniform, or halving (1/2, 1/4, ..., the last two equal)
-static size_t chunk_first_unit(size_t U, int K, int c, bool halving) {
+// first unit of chunk c of K over U units
+static size_t chunk_first_unit(size_t U, int K, int c, bool geometric) {
   if (c <= 0) return 0;
   if (c >= K) return U;
-  if (!halving || K < 3) return (size_t)(((unsigned __int128)U * (unsigned)c) / (unsigned)K);
-  // sum_{i<c} 2^-(i+1) = 1 - 2^-c
-  return U - (U >> c);
+  if (!geometric) return (size_t)(((unsigned __int128)U * (unsigned)c) / (unsigned)K);
+  const size_t f = (size_t)((double)U * chunk_cum(K, c));
+  return f > U ? U : f;
 }
 
 template <class FA, class FB>
@@ -1054,7 +1063,7 @@ static int semilag_impl(const tbslas_field *f1, const tbslas_field *f2, tbslas_t
     return run_host_pipeline(
         ctx, sp, n,
         [&](PipeBufs &B, size_t m, size_t off) {
-          return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk, B.pos, con, off / P, true);
+          return traj_rk2_dev(f1, f2, bc, B.pos, B.tmp, m, tinit, tfinal, nrk, B.pos, con, off / P, true, n);
         },
         [&](PipeBufs &B, size_t m, size_t) { return eval_tree_dev(con, bc, B.pos, m, EPI_STORE, B.val, nullptr, 0.0, nullptr); });
   }

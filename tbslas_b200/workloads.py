@@ -95,7 +95,21 @@ def _fit_scalar(coord, depth, q, fn, device=None, chunk=2048):
 
 
 def make(name: str, device=None, scale: int = 0) -> Workload:
-    """scale > 0 shrinks the workload (max depth reduced by `scale`) for tests."""
+    """scale > 0 shrinks the workload (max depth reduced by `scale`) for tests.
+
+    The host BLAS/LAPACK behind the fits (pinv, matmul) runs single-threaded here: its rounding
+    depends on the thread count, and `torchrun` sets OMP_NUM_THREADS=1 -- without the limit the
+    N = 1 bench and the N = 2, 4, 8 benches would advect coefficient sets that differ in the last
+    bits and their checksums could not be compared."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:  # pragma: no cover
+        return _make(name, device, scale)
+    with threadpool_limits(limits=1):
+        return _make(name, device, scale)
+
+
+def _make(name: str, device=None, scale: int = 0) -> Workload:
     name = name.lower()
     if name == "c1":
         q, depth = 8, max(1, 4 - scale)
