@@ -236,6 +236,8 @@ int tbslas_b200_semilag_insitu_dep(const tbslas_field *f1, const tbslas_field *f
  * at the new_nodes grid).  Supplied by the caller once per degree so that host and device
  * refits use the very same matrix; kept on the device by the context. */
 int tbslas_b200_set_pt2coeff(tbslas_ctx *ctx, int q, const double *M);
+/* Whether THIS context already holds the matrix of degree q (the C++ adaptor uploads it on first use). */
+int tbslas_b200_has_pt2coeff(tbslas_ctx *ctx, int q, int *has);
 /* coeff[leaf][dof][:] = vals[leaf][dof][:] * M  for every local leaf, written into the tree
  * (one FP64 tensor-core GEMM).  point_major = 0: vals is [leaf][dof][P], the layout
  * SetTreeGridValues consumes; 1: vals is [leaf*P][dof], the layout SolveSemilagRK2 produces
@@ -253,6 +255,16 @@ int tbslas_b200_semilag_insitu_update(const tbslas_field *f1, const tbslas_field
 /* grid [dof][n_reg][n_reg][n_reg] (x fastest), node centred on [0,1]^3. */
 int tbslas_b200_cubic_eval(tbslas_ctx *ctx, const double *grid, int n_reg, int dof,
                            const double *pos, size_t n, double *out, int mem);
+/* The same with the grid RESIDENT in HBM: the reference's caller samples a field onto the regular
+ * grid once and interpolates from it many times (tree_functor.h:89-153 takes the grid by pointer);
+ * here the upload (403 MB at 256^3 x dof 3) is paid once per grid, not once per call.  grid_eval with
+ * host buffers streams the queries in and the values out in overlapping chunks. */
+typedef struct tbslas_grid tbslas_grid;
+int tbslas_b200_grid_create(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, int mem,
+                            tbslas_grid **out);
+int tbslas_b200_grid_update(tbslas_grid *g, const double *grid, int mem);
+int tbslas_b200_grid_eval(tbslas_grid *g, const double *pos, size_t n, double *out, int mem);
+int tbslas_b200_grid_destroy(tbslas_grid *g);
 
 /* ---- either side of the path ("next" rows) -------------------------------- */
 /* tbslas::CollectChebTreeGridPoints (tree_utils.h:442-498): arrival points of the
@@ -280,6 +292,18 @@ int tbslas_b200_partition_leaves(size_t n_leaf, int nranks, size_t *first);
  * (tree_utils.h:672-675).  first[r] = first leaf of rank r, first[nranks] = n_leaf.  Host only. */
 int tbslas_b200_partition_leaves_weighted(size_t n_leaf, const double *weight, int nranks,
                                           size_t *first);
+/* Moves the leaves of a Morton-sharded tree between the ranks -- keys, geometry, integer boxes and
+ * coefficient blocks, device to device over NCCL -- so that rank r owns the global leaves
+ * [new_first[r], new_first[r+1]) (new_first[0] = 0, new_first[nranks] = total leaves), and rebuilds the
+ * split keys: what tbslas::SemiMergeTree does through PVFMM's RedistNodes when it re-balances by last
+ * step's point counts (tree_utils.h:609-729).  Collective; every rank passes the same array.  Results of
+ * evaluations are unchanged bit for bit (a point is evaluated by the leaf that contains it, wherever
+ * that leaf lives).  Typical use: weights = tree_last_point_counts gathered over the ranks ->
+ * partition_leaves_weighted -> tree_reshard for the advected tree, and again with the same split keys
+ * for the trees evaluated with it. */
+int tbslas_b200_tree_reshard(tbslas_tree *tree, const size_t *new_first);
+/* Global index of this rank's first leaf and the number of leaves over all ranks. */
+int tbslas_b200_tree_global_range(const tbslas_tree *tree, size_t *first, size_t *total);
 /* Points that the most recent evaluation of `tree` located in each of its LOCAL leaves -- this
  * rank's own points plus those received from other ranks (the part_indx differences of
  * tree_functor.h:190-198), [n_leaf]: the weights above.  TBSLAS_ERR_INVALID before the first

@@ -331,24 +331,25 @@ void SolveSemilagRK2(VFunctor &vel_evaluator, EFunctor &extrap_evaluator,
 // tree_utils.h:442-498), advected, and refitted with the reference's own point-to-coefficient
 // matrix (GetPt2CoeffMatrix, cheb.h:166-196, uploaded once per degree) by one tensor-core
 // GEMM (SetTreeGridValues, tree_utils.h:500-552); only the new coefficients come back.
-template <class TreeType, class TreeFunc>
-void SolveSemilagInSitu(TreeFunc &tvel_func, TreeType &tree_curr, const int timestep,
-                        const typename TreeType::Real_t dt, int num_rk_step = 1, bool /*adaptive*/ = true) {
+namespace detail {
+// steps (1)-(3) of tbslas::SolveSemilagInSitu on the device; f2 == nullptr: one-functor form
+template <class TreeType>
+void SemilagInSituImpl(const tbslas_field *f1, const tbslas_field *f2, TreeType &tree_curr, const int timestep,
+                       const typename TreeType::Real_t dt, int num_rk_step) {
   typedef typename TreeType::Real_t RealType;
   typedef typename TreeType::Node_t NodeType;
   NodeFieldFunctor<RealType, TreeType> con(&tree_curr);
   DeviceTree<TreeType> &dcon = con.device_tree();
   const Context &ctx = dcon.context();
   const int q = dcon.cheb_deg(), dof = dcon.dof();
-  static int uploaded_q = -1;
-  if (uploaded_q != q) {
+  int has = 0;  // per context, not per process: a second Context needs its own copy of the matrix
+  ctx.check(tbslas_b200_has_pt2coeff(ctx.get(), q, &has));
+  if (!has) {
     pvfmm::Matrix<RealType> M;
     tbslas::GetPt2CoeffMatrix<RealType>(q, M);
     ctx.check(tbslas_b200_set_pt2coeff(ctx.get(), q, &M[0][0]));
-    uploaded_q = q;
   }
-  ctx.check(tbslas_b200_semilag_insitu_update(&tvel_func.field, nullptr, dcon.get(), CurrentBC(), timestep, dt,
-                                              num_rk_step));
+  ctx.check(tbslas_b200_semilag_insitu_update(f1, f2, dcon.get(), CurrentBC(), timestep, dt, num_rk_step));
   const size_t nc = (size_t)(q + 1) * (q + 2) * (q + 3) / 6 * dof;
   std::vector<RealType> coeff(nc * dcon.n_leaf());
   ctx.check(tbslas_b200_tree_get_coeff(dcon.get(), coeff.data(), TBSLAS_MEM_HOST));
@@ -359,6 +360,26 @@ void SolveSemilagInSitu(TreeFunc &tvel_func, TreeType &tree_curr, const int time
       std::memcpy(&(all[i]->ChebData()[0]), &coeff[j * nc], nc * sizeof(RealType));
       j++;
     }
+}
+}  // namespace detail
+
+// NOTE on dof > 1: the values of a step are point-major [point][dof] (SolveSemilagRK2's layout) and the
+// refit here reads them as such.  The reference's own SolveSemilagInSitu hands that array to
+// SetTreeGridValues, which reads [dof][P] per leaf (tree_semilag.h:124-133 vs tree_utils.h:528-547) --
+// right for dof = 1 only; its dof-3 caller (tree_ns.h:502-513) transposes by hand first.  So for dof > 1
+// this overload returns what the NS call pattern returns, not what the reference's in-situ template does.
+template <class TreeType, class TreeFunc>
+void SolveSemilagInSitu(TreeFunc &tvel_func, TreeType &tree_curr, const int timestep,
+                        const typename TreeType::Real_t dt, int num_rk_step = 1, bool /*adaptive*/ = true) {
+  detail::SemilagInSituImpl(&tvel_func.field, (const tbslas_field *)nullptr, tree_curr, timestep, dt, num_rk_step);
+}
+
+// The two-functor form (tree_semilag.h:137-181; drivers advtvextrap.cpp, ns.cpp): stage 1 of every RK2
+// sub-step samples tvel_func, stage 2 the extrapolation tvel_extrap (traj.inc:71-92).
+template <class TreeType, class TreeFunc, class TreeExtrap>
+void SolveSemilagInSitu(TreeFunc &tvel_func, TreeExtrap &tvel_extrap, TreeType &tree_curr, const int timestep,
+                        const typename TreeType::Real_t dt, int num_rk_step = 1, bool /*adaptive*/ = true) {
+  detail::SemilagInSituImpl(&tvel_func.field, &tvel_extrap.field, tree_curr, timestep, dt, num_rk_step);
 }
 #endif
 

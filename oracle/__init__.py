@@ -179,7 +179,9 @@ class Oracle:
         return out, p
 
     def traj_rk2(self, vel, pos, tinit, tfinal, nrk, bc, kind="steady", times=None):
-        """vel: tree handle (steady), 4 handles (set4) or (tp, tc) (extrap)."""
+        """vel: tree handle (steady), 4 handles (set4), (tp, tc) (extrap: first stage samples tc,
+        second the extrapolation) or (t1, t2) (pair: first stage samples t1, second t2 -- the
+        second trajectory of the NS call pattern, tree_ns.h:479-483; port only)."""
         p = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
         n = p.shape[0]
         out = np.empty((n, 3))
@@ -188,6 +190,8 @@ class Oracle:
                 f1, f2 = self._field(0, [vel]), None
             elif kind == "set4":
                 f1, f2 = self._field(1, vel, times), None
+            elif kind == "pair":
+                f1, f2 = self._field(0, [vel[0]]), self._field(0, [vel[1]])
             else:  # first stage samples tc, second the extrapolation (traj.inc:71-92)
                 f1, f2 = self._field(0, [vel[1]]), self._field(2, [vel[0], vel[1]])
             self.lib.orc_traj_rk2(C.byref(f1), C.byref(f2) if f2 else None, bc, _d(p), n,

@@ -13,8 +13,10 @@
 //   (C) tbslas::b200 fused overloads with the reference's signatures (one C-ABI call/step)
 // for SolveSemilagRK2 (semilag.inc:27-45), ComputeTrajRK2 with a FieldSetFunctor
 // (traj.inc:49-68, tree_set_functor.h:49-79), the extrapolated two-functor form
-// (traj.inc:95-115) and the tree-level SolveSemilagInSitu (tree_semilag.h:92-135).
-// Bar: max |B - A| and |C - A| <= 1e-11 of the field scale (FMA vs mul+add accumulation).
+// (traj.inc:95-115), the tree-level SolveSemilagInSitu in its one- and two-functor forms
+// (tree_semilag.h:92-135, :137-181) and the Navier-Stokes call pattern (tree_ns.h:466-518: two
+// trajectories from the same arrival points, dof-3 advected field, 2/dt*c - 0.5/dt*p, refit).
+// Bars: trajectories 1e-12; composed steps 1e-11 of the field scale (see kStepTol).
 #include <mpi.h>
 #include <omp.h>
 
@@ -113,6 +115,11 @@ static double maxdiff(const std::vector<double> &a, const std::vector<double> &b
   return m;
 }
 
+// Bars, relative to the field scale.  A composed step (trajectory, then the advected field AT the
+// departure point) carries the departure point's last-bit difference times the field's steepness: the
+// test fields here are pseudo-random polynomials of degree 6 (gradients of O(10..100)), so the composed
+// bar is 1e-11 while trajectories are held to 1e-12; the NS pattern multiplies by 2/dt = 32 on top.
+static const double kStepTol = 1e-11, kNsTol = 1e-10;
 static int n_fail = 0;
 static void report(const char *what, double err, double tol) {
   printf("  %-58s %.3e  %s\n", what, err, err <= tol ? "ok" : "FAIL");
@@ -140,8 +147,8 @@ int main() {
       tbslas::SolveSemilagRK2(gvel, gcon, pos, 3, timestep, dt, nrk, b);  // reference template, GPU functors
       tbslas::b200::SolveSemilagRK2(gvel, gcon, pos, 3, timestep, dt, nrk, c);
       const double sc = maxabs(a);
-      report("SolveSemilagRK2: reference template over b200 functors", maxdiff(a, b) / sc, 1e-11);
-      report("SolveSemilagRK2: b200 fused overload", maxdiff(a, c) / sc, 1e-11);
+      report("SolveSemilagRK2: reference template over b200 functors", maxdiff(a, b) / sc, kStepTol);
+      report("SolveSemilagRK2: b200 fused overload", maxdiff(a, c) / sc, kStepTol);
       report("                 fused == functor-by-functor (bitwise)", maxdiff(b, c), 0.0);
 
       // ---- time-varying velocity: FieldSetFunctor (advtv.cpp:171-190,301)
@@ -187,8 +194,91 @@ int main() {
           cb.push_back(con_g->GetNodeList()[l]->ChebData()[k]);
           cc.push_back(con_f->GetNodeList()[l]->ChebData()[k]);
         }
-      report("SolveSemilagInSitu coefficients: reference template", maxdiff(ca, cb) / maxabs(ca), 1e-11);
-      report("SolveSemilagInSitu coefficients: b200 in-situ", maxdiff(ca, cc) / maxabs(ca), 1e-11);
+      report("SolveSemilagInSitu coefficients: reference template", maxdiff(ca, cb) / maxabs(ca), kStepTol);
+      report("SolveSemilagInSitu coefficients: b200 in-situ", maxdiff(ca, cc) / maxabs(ca), kStepTol);
+
+      // ---- the two-functor tree-level step (tree_semilag.h:137-181; advtvextrap.cpp, ns.cpp)
+      Tree_t *c2_r = make_tree(depth, q, 1, 7, 1.0), *c2_g = make_tree(depth, q, 1, 7, 1.0),
+             *c2_f = make_tree(depth, q, 1, 7, 1.0);
+      tbslas::SolveSemilagInSitu(rcur, rext, *c2_r, timestep, dt, nrk);
+      tbslas::SolveSemilagInSitu(gcur, gext, *c2_g, timestep, dt, nrk);        // reference template, GPU functors
+      tbslas::b200::SolveSemilagInSitu(gcur, gext, *c2_f, timestep, dt, nrk);  // one C-ABI call + read-back
+      ca.clear(), cb.clear(), cc.clear();
+      for (size_t l = 0; l < c2_r->GetNodeList().size(); l++)
+        for (size_t k = 0; k < c2_r->GetNodeList()[l]->ChebData().Dim(); k++) {
+          ca.push_back(c2_r->GetNodeList()[l]->ChebData()[k]);
+          cb.push_back(c2_g->GetNodeList()[l]->ChebData()[k]);
+          cc.push_back(c2_f->GetNodeList()[l]->ChebData()[k]);
+        }
+      report("SolveSemilagInSitu(v, extrap): reference template", maxdiff(ca, cb) / maxabs(ca), kStepTol);
+      report("SolveSemilagInSitu(v, extrap): b200 in-situ", maxdiff(ca, cc) / maxabs(ca), kStepTol);
+
+      // ---- the Navier-Stokes call pattern (tree_ns.h:466-518): the advected field is the dof-3
+      // velocity itself; two backward trajectories from the same arrival points,
+      //   [t, t-dt]  stage 1 = v^n,     stage 2 = extrapolation;  sample v^n     there
+      //   [t, t-2dt] stage 1 = v^{n-1}, stage 2 = v^n;            sample v^{n-1} there
+      // combined 2/dt * c - 0.5/dt * p, transposed point-major -> dof-major per leaf, refitted.
+      {
+        const double tcurr = timestep * dt, ccoeff = 2.0 / dt, pcoeff = -0.5 / dt;
+        const int P = (q + 1) * (q + 1) * (q + 1), dof = 3;
+        Tree_t *vp[2] = {make_tree(depth, q, 3, 9, 1.0), make_tree(depth, q, 3, 9, 1.0)};   // v^{n-1}: rough field
+        Tree_t *vc[2] = {make_tree(depth, q, 3, 11, 1.0), make_tree(depth, q, 3, 11, 1.0)}; // v^n
+        Tree_t *tn[2] = {make_tree(depth, q, 3, 11, 1.0), make_tree(depth, q, 3, 11, 1.0)}; // tree that receives the result
+        std::vector<double> res[2];
+        for (int side = 0; side < 2; side++) {  // 0: reference functors (CPU), 1: b200 functors (GPU)
+          std::vector<double> arr, dep, cval, pval;
+          const int num_leaf = tbslas::CollectChebTreeGridPoints(*tn[side], arr);
+          const int np = arr.size() / 3;
+          dep.resize(arr.size());
+          cval.resize((size_t)np * dof);
+          pval.resize((size_t)np * dof);
+          if (side == 0) {
+            tbslas::NodeFieldFunctor<double, Tree_t> fp(vp[0]), fc(vc[0]);
+            tbslas::FieldExtrapFunctor<double, Tree_t> fe(vp[0], vc[0]);
+            tbslas::ComputeTrajRK2(fc, fe, arr, tcurr, tcurr - dt, nrk, dep);
+            fc(dep.data(), np, cval.data());
+            tbslas::ComputeTrajRK2(fp, fc, arr, tcurr, tcurr - dt * 2, nrk, dep);
+            fp(dep.data(), np, pval.data());
+          } else {
+            tbslas::b200::NodeFieldFunctor<double, Tree_t> fp(vp[1]), fc(vc[1]);
+            tbslas::b200::FieldExtrapFunctor<double, Tree_t> fe(vp[1], vc[1]);
+            tbslas::ComputeTrajRK2(fc, fe, arr, tcurr, tcurr - dt, nrk, dep);   // the reference's template
+            fc(dep.data(), np, cval.data());
+            tbslas::b200::ComputeTrajRK2(fp, fc, arr, tcurr, tcurr - dt * 2, nrk, dep);  // fused overload
+            fp(dep.data(), np, pval.data());
+          }
+          std::vector<double> val((size_t)np * dof), ml((size_t)np * dof);
+          for (size_t i = 0; i < val.size(); i++) val[i] = ccoeff * cval[i] + pcoeff * pval[i];
+          for (int nindx = 0; nindx < num_leaf; nindx++) {
+            const size_t shift = (size_t)nindx * P * dof;
+            for (int j = 0; j < P; j++)
+              for (int i = 0; i < dof; i++) ml[shift + j + (size_t)i * P] = val[shift + (size_t)j * dof + i];
+          }
+          if (side == 0) {
+            tbslas::SetTreeGridValues(*tn[0], q, dof, ml);
+          } else {  // device refit through the C ABI: the dof-major layout SetTreeGridValues consumes
+            tbslas::b200::NodeFieldFunctor<double, Tree_t> fn(tn[1]);
+            tbslas::b200::DeviceTree<Tree_t> &dn = fn.device_tree();
+            int has = 0;
+            dn.context().check(tbslas_b200_has_pt2coeff(dn.context().get(), q, &has));
+            if (!has) {
+              pvfmm::Matrix<double> M;
+              tbslas::GetPt2CoeffMatrix<double>(q, M);
+              dn.context().check(tbslas_b200_set_pt2coeff(dn.context().get(), q, &M[0][0]));
+            }
+            dn.context().check(tbslas_b200_tree_set_grid_values(dn.get(), ml.data(), /*point_major=*/0, TBSLAS_MEM_HOST));
+            std::vector<double> coeff((size_t)ncoef(q) * dof * num_leaf);
+            dn.context().check(tbslas_b200_tree_get_coeff(dn.get(), coeff.data(), TBSLAS_MEM_HOST));
+            for (int l = 0; l < num_leaf; l++)
+              for (long k = 0; k < ncoef(q) * dof; k++) tn[1]->GetNodeList()[l]->ChebData()[k] = coeff[(size_t)l * ncoef(q) * dof + k];
+          }
+          for (size_t l = 0; l < tn[side]->GetNodeList().size(); l++)
+            for (size_t k = 0; k < tn[side]->GetNodeList()[l]->ChebData().Dim(); k++)
+              res[side].push_back(tn[side]->GetNodeList()[l]->ChebData()[k]);
+        }
+        report("NS pattern (2 trajectories, dof 3, 2/dt c - 0.5/dt p, refit)", maxdiff(res[0], res[1]) / maxabs(res[0]),
+               kNsTol);
+      }
     }
   } catch (const std::exception &e) {
     printf("EXCEPTION: %s\n", e.what());

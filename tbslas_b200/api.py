@@ -186,6 +186,10 @@ class Context:
         self.check(self.lib.tbslas_b200_cubic_eval(self.h, ga, n_reg, dof, pa, n, oa, pm))
         return out
 
+    def grid(self, grid, dof: int, n_reg: int) -> "CubicGrid":
+        """A uniform grid [dof][n_reg]^3 kept resident in HBM (tbslas_b200_grid_create)."""
+        return CubicGrid(self, grid, dof, n_reg)
+
     # -- instrumentation ------------------------------------------------------
     def profile_enable(self, on: bool = True) -> None:
         self.check(self.lib.tbslas_b200_profile_enable(self.h, int(on)))
@@ -210,6 +214,34 @@ class Context:
         v = C.c_double()
         self.check(self.lib.tbslas_b200_fp64_peak(self.h, reps, C.byref(v)))
         return v.value
+
+
+class CubicGrid:
+    """Resident uniform grid for tbslas::fast_interp (tree_functor.h:89-153)."""
+
+    def __init__(self, ctx: Context, grid, dof: int, n_reg: int):
+        self.ctx, self.dof, self.n_reg = ctx, int(dof), int(n_reg)
+        a, m = _addr(grid)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.tbslas_b200_grid_create(ctx.h, a, self.n_reg, self.dof, m, C.byref(h)))
+        self.h = h
+
+    def update(self, grid) -> None:
+        a, m = _addr(grid)
+        self.ctx.check(self.ctx.lib.tbslas_b200_grid_update(self.h, a, m))
+
+    def __call__(self, pts, out=None):
+        n = pts.shape[0]
+        if out is None:
+            out = _like(pts, (n, self.dof))
+        pa, pm = _addr(pts)
+        self.ctx.check(self.ctx.lib.tbslas_b200_grid_eval(self.h, pa, n, _addr(out)[0], pm))
+        return out
+
+    def destroy(self) -> None:
+        if self.h:
+            self.ctx.lib.tbslas_b200_grid_destroy(self.h)
+            self.h = None
 
 
 class Tree:
@@ -240,6 +272,21 @@ class Tree:
         if self.h:
             self.ctx.lib.tbslas_b200_tree_destroy(self.h)
             self.h = None
+
+    def reshard(self, new_first) -> None:
+        """Collective: move leaves between ranks so that rank r owns global leaves
+        [new_first[r], new_first[r+1]) (tbslas_b200_tree_reshard)."""
+        arr = (C.c_size_t * len(new_first))(*[int(x) for x in new_first])
+        self.ctx.check(self.ctx.lib.tbslas_b200_tree_reshard(self.h, arr))
+        q, dof, n = C.c_int(), C.c_int(), C.c_size_t()
+        self.ctx.check(self.ctx.lib.tbslas_b200_tree_info(self.h, C.byref(q), C.byref(dof), C.byref(n)))
+        self.n_leaf = int(n.value)
+
+    def global_range(self):
+        """-> (global index of this rank's first leaf, leaves over all ranks)."""
+        a, b = C.c_size_t(), C.c_size_t()
+        self.ctx.check(self.ctx.lib.tbslas_b200_tree_global_range(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def set_grid_values(self, vals, point_major: bool = False) -> None:
         """tbslas::SetTreeGridValues (tree_utils.h:500-552): refit the coefficients from grid

@@ -28,11 +28,12 @@ SYMBOLS = [
     "tbslas_b200_tree_create", "tbslas_b200_tree_create_replicated", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_get_coeff", "tbslas_b200_tree_destroy",
     "tbslas_b200_tree_info", "tbslas_b200_eval", "tbslas_b200_eval_set4",
     "tbslas_b200_eval_extrap", "tbslas_b200_eval_field", "tbslas_b200_traj_rk2",
-    "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_semilag_insitu_dep", "tbslas_b200_set_pt2coeff",
-    "tbslas_b200_tree_set_grid_values", "tbslas_b200_semilag_insitu_update", "tbslas_b200_cubic_eval", "tbslas_b200_collect_grid_points",
+    "tbslas_b200_semilag_rk2", "tbslas_b200_semilag_insitu", "tbslas_b200_semilag_insitu_dep", "tbslas_b200_set_pt2coeff", "tbslas_b200_has_pt2coeff",
+    "tbslas_b200_tree_set_grid_values", "tbslas_b200_semilag_insitu_update", "tbslas_b200_cubic_eval", "tbslas_b200_grid_create", "tbslas_b200_grid_update", "tbslas_b200_grid_eval",
+    "tbslas_b200_grid_destroy", "tbslas_b200_collect_grid_points",
     "tbslas_b200_new_nodes", "tbslas_b200_point_key", "tbslas_b200_owner_of_key",
     "tbslas_b200_partition_leaves", "tbslas_b200_partition_leaves_weighted",
-    "tbslas_b200_tree_last_point_counts", "tbslas_b200_tree_tail_norm", "tbslas_b200_profile_enable", "tbslas_b200_profile_reset",
+    "tbslas_b200_tree_reshard", "tbslas_b200_tree_global_range", "tbslas_b200_tree_last_point_counts", "tbslas_b200_tree_tail_norm", "tbslas_b200_profile_enable", "tbslas_b200_profile_reset",
     "tbslas_b200_profile_num_stages", "tbslas_b200_profile_stage_name",
     "tbslas_b200_profile_get", "tbslas_b200_kernel_launches", "tbslas_b200_fp64_peak",
 ]
@@ -55,11 +56,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("TBSLAS_B200_LIB") or LIB_PATH  # A/B builds of the same library (build.py --variant)
+    if not os.path.exists(path):
         raise TbslasError(
             "%s not found: build it with `python -m tbslas_b200.build` (there is no CPU "
-            "fallback)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+            "fallback)" % path)
+    L = C.CDLL(path)
     vp, dp, i32p = C.c_void_p, C.c_void_p, C.c_void_p  # raw addresses (host or device)
     sz = C.c_size_t
     L.tbslas_b200_init.argtypes = [C.c_int, C.POINTER(vp)]
@@ -105,10 +107,15 @@ def load() -> C.CDLL:
     L.tbslas_b200_semilag_insitu_dep.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int,
                                                  C.c_int, C.c_double, C.c_int, dp, dp, C.c_int]
     L.tbslas_b200_set_pt2coeff.argtypes = [vp, C.c_int, dp]
+    L.tbslas_b200_has_pt2coeff.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     L.tbslas_b200_tree_set_grid_values.argtypes = [vp, dp, C.c_int, C.c_int]
     L.tbslas_b200_semilag_insitu_update.argtypes = [C.POINTER(Field), C.POINTER(Field), vp, C.c_int,
                                                     C.c_int, C.c_double, C.c_int]
     L.tbslas_b200_cubic_eval.argtypes = [vp, dp, C.c_int, C.c_int, dp, sz, dp, C.c_int]
+    L.tbslas_b200_grid_create.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.tbslas_b200_grid_update.argtypes = [vp, dp, C.c_int]
+    L.tbslas_b200_grid_eval.argtypes = [vp, dp, sz, dp, C.c_int]
+    L.tbslas_b200_grid_destroy.argtypes = [vp]
     L.tbslas_b200_collect_grid_points.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_new_nodes.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.tbslas_b200_point_key.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
@@ -116,6 +123,8 @@ def load() -> C.CDLL:
     L.tbslas_b200_owner_of_key.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
     L.tbslas_b200_partition_leaves.argtypes = [sz, C.c_int, C.POINTER(sz)]
     L.tbslas_b200_partition_leaves_weighted.argtypes = [sz, C.POINTER(C.c_double), C.c_int, C.POINTER(sz)]
+    L.tbslas_b200_tree_reshard.argtypes = [vp, C.POINTER(sz)]
+    L.tbslas_b200_tree_global_range.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
     L.tbslas_b200_tree_last_point_counts.argtypes = [vp, vp, C.c_int]
     L.tbslas_b200_tree_tail_norm.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_profile_enable.argtypes = [vp, C.c_int]

@@ -100,6 +100,7 @@ int px_packed(tbslas_ctx *ctx);
 int px_finish(tbslas_tree *t, int bc, const uint32_t *send_idx, size_t n_local, int epilogue, double *out,
               const double *base, double alpha, int32_t *leaf_out);
 void comm_destroy(tbslas_ctx *ctx);
+int comm_reshard(tbslas_tree *t, const size_t *new_first);
 
 // ---------------------------------------------------------------------------
 // one tree evaluation on device buffers (tbslas::EvalTree, tree_functor.h:397-690)
@@ -602,6 +603,98 @@ static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA p
   return comm_check(ctx);
 }
 
+// Everything a tree derives from its leaf list (host coordinates + depths, Morton order): keys,
+// geometry, integer boxes, the locate kernel's cell table, hashes.  Replaces the arrays the tree
+// holds (used by tree_create and, after leaves moved between ranks, by tree_reshard); the
+// coefficient block is (re)allocated and zeroed only when `alloc_coeff`.
+int tree_build_structure(tbslas_tree *t, const std::vector<double> &hc, const std::vector<uint8_t> &hd,
+                         bool alloc_coeff) {
+  tbslas_ctx *ctx = t->ctx;
+  const size_t n_leaf = hd.size();
+  std::vector<uint64_t> hk(n_leaf);
+  std::vector<double4> hg(n_leaf + 1);
+  std::vector<uint4> hb(n_leaf + 1);
+  bool boxes_ok = true;
+  for (size_t j = 0; j < n_leaf; j++) {
+    if (hd[j] > kMaxDepth) return fail(ctx, TBSLAS_ERR_INVALID, "leaf %zu: depth %d > 15", j, hd[j]);
+    hk[j] = leaf_key(hc[3 * j], hc[3 * j + 1], hc[3 * j + 2]);
+    if (hk[j] == ~0ull) return fail(ctx, TBSLAS_ERR_INVALID, "leaf %zu: corner outside [0,1)^3", j);
+    if (j && !(hk[j - 1] < hk[j]))
+      return fail(ctx, TBSLAS_ERR_INVALID, "leaves must be in strictly ascending Morton order (leaf %zu)", j);
+    // (x - c) * 2.0 * s, s = 2^depth (tree_functor.h:285-293): 2*s is exact
+    hg[j] = make_double4(hc[3 * j], hc[3 * j + 1], hc[3 * j + 2], 2.0 * (double)(1ull << hd[j]));
+    // integer box of the octant (locate fast path): usable when every leaf is aligned to its
+    // own depth and ends before the next leaf begins
+    const unsigned sh = (unsigned)(kMaxDepth - hd[j]);
+    hb[j] = make_uint4((unsigned)floor(hc[3 * j] * 32768.0), (unsigned)floor(hc[3 * j + 1] * 32768.0),
+                       (unsigned)floor(hc[3 * j + 2] * 32768.0), sh);
+    const unsigned low = (1u << sh) - 1u;
+    if ((hb[j].x | hb[j].y | hb[j].z) & low) boxes_ok = false;
+    if (j && hk[j] - hk[j - 1] < (1ull << (3 * hb[j - 1].w))) boxes_ok = false;
+  }
+  hg[n_leaf] = make_double4(0, 0, 0, 2.0);  // null leaf: zero coefficients
+  hb[n_leaf] = make_uint4(0, 0, 0, 0);
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(t->d_key);
+  cudaFree(t->d_geom);
+  cudaFree(t->d_depth);
+  cudaFree(t->d_box);
+  cudaFree(t->d_cell);
+  cudaFree(t->d_pt_count);
+  t->d_key = nullptr, t->d_geom = nullptr, t->d_depth = nullptr, t->d_box = nullptr, t->d_cell = nullptr;
+  t->d_pt_count = nullptr;
+  t->pt_count_valid = false;
+  t->n_leaf = n_leaf;
+  TB_CUDA(ctx, cudaMalloc(&t->d_key, sizeof(uint64_t) * (n_leaf + 1)));
+  TB_CUDA(ctx, cudaMalloc(&t->d_geom, sizeof(double4) * (n_leaf + 1)));
+  TB_CUDA(ctx, cudaMalloc(&t->d_depth, n_leaf + 1));
+  TB_CUDA(ctx, cudaMalloc(&t->d_box, sizeof(uint4) * (n_leaf + 1)));
+  TB_CUDA(ctx, cudaMemcpy(t->d_box, hb.data(), sizeof(uint4) * (n_leaf + 1), cudaMemcpyHostToDevice));
+  t->boxes_ok = boxes_ok;
+  t->boxes_all = boxes_ok;
+  {  // cell table: depth g with about two cells per leaf, 1 <= g <= 6 (1 MiB)
+    int g = 1;
+    while (g < 6 && ((size_t)1 << (3 * g)) < 2 * n_leaf) g++;
+    const size_t n_cell = (size_t)1 << (3 * g);
+    t->cell_shift = 3 * (kMaxDepth - g);
+    std::vector<uint32_t> cell(n_cell + 2);
+    size_t j = 0;
+    for (size_t c = 0; c < n_cell; c++) {
+      const uint64_t first = (uint64_t)c << t->cell_shift;
+      while (j < n_leaf && hk[j] <= first) j++;
+      cell[c] = (uint32_t)j;
+    }
+    cell[n_cell] = cell[n_cell + 1] = (uint32_t)n_leaf;
+    TB_CUDA(ctx, cudaMalloc(&t->d_cell, sizeof(uint32_t) * cell.size()));
+    TB_CUDA(ctx, cudaMemcpy(t->d_cell, cell.data(), sizeof(uint32_t) * cell.size(), cudaMemcpyHostToDevice));
+  }
+  {
+    uint64_t h = 1469598103934665603ull;  // FNV-1a over the leaf keys and depths
+    for (size_t j = 0; j < n_leaf; j++) {
+      h = (h ^ hk[j]) * 1099511628211ull;
+      h = (h ^ hd[j]) * 1099511628211ull;
+    }
+    t->struct_hash = h;
+    t->global_hash = h;
+  }
+  t->n_leaf_max = n_leaf;
+  t->n_leaf_global = n_leaf;
+  t->leaf_offset = 0;
+  t->rank_first.assign({(size_t)0, n_leaf});
+  TB_CUDA(ctx, cudaMemcpy(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice));
+  TB_CUDA(ctx, cudaMemcpy(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice));
+  TB_CUDA(ctx, cudaMemcpy(t->d_depth, hd.data(), n_leaf, cudaMemcpyHostToDevice));
+  if (alloc_coeff) {
+    cudaFree(t->d_coeff);
+    t->d_coeff = nullptr;
+    TB_CUDA(ctx, cudaMalloc(&t->d_coeff, sizeof(double) * t->stride * (n_leaf + 1)));
+    TB_CUDA(ctx, cudaMemset(t->d_coeff, 0, sizeof(double) * t->stride * (n_leaf + 1)));
+  }
+  t->first_key = n_leaf ? hk[0] : ~0ull;
+  t->splitters.assign(1, t->first_key);
+  return TBSLAS_OK;
+}
+
 }  // namespace tb
 
 using namespace tb;
@@ -757,34 +850,10 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
     memcpy(hc.data(), coord, sizeof(double) * 3 * n_leaf);
     memcpy(hd.data(), depth, n_leaf);
   }
-  std::vector<uint64_t> hk(n_leaf);
-  std::vector<double4> hg(n_leaf + 1);
-  std::vector<uint4> hb(n_leaf + 1);
-  bool boxes_ok = true;
-  for (size_t j = 0; j < n_leaf; j++) {
-    if (hd[j] > kMaxDepth) return fail(ctx, TBSLAS_ERR_INVALID, "leaf %zu: depth %d > 15", j, hd[j]);
-    hk[j] = leaf_key(hc[3 * j], hc[3 * j + 1], hc[3 * j + 2]);
-    if (hk[j] == ~0ull) return fail(ctx, TBSLAS_ERR_INVALID, "leaf %zu: corner outside [0,1)^3", j);
-    if (j && !(hk[j - 1] < hk[j]))
-      return fail(ctx, TBSLAS_ERR_INVALID, "leaves must be in strictly ascending Morton order (leaf %zu)", j);
-    // (x - c) * 2.0 * s, s = 2^depth (tree_functor.h:285-293): 2*s is exact
-    hg[j] = make_double4(hc[3 * j], hc[3 * j + 1], hc[3 * j + 2], 2.0 * (double)(1ull << hd[j]));
-    // integer box of the octant (locate fast path): usable when every leaf is aligned to its
-    // own depth and ends before the next leaf begins
-    const unsigned sh = (unsigned)(kMaxDepth - hd[j]);
-    hb[j] = make_uint4((unsigned)floor(hc[3 * j] * 32768.0), (unsigned)floor(hc[3 * j + 1] * 32768.0),
-                       (unsigned)floor(hc[3 * j + 2] * 32768.0), sh);
-    const unsigned low = (1u << sh) - 1u;
-    if ((hb[j].x | hb[j].y | hb[j].z) & low) boxes_ok = false;
-    if (j && hk[j] - hk[j - 1] < (1ull << (3 * hb[j - 1].w))) boxes_ok = false;
-  }
-  hg[n_leaf] = make_double4(0, 0, 0, 2.0);  // null leaf: zero coefficients
-  hb[n_leaf] = make_uint4(0, 0, 0, 0);
   tbslas_tree *t = new tbslas_tree();
   t->ctx = ctx;
   t->q = q;
   t->dof = dof;
-  t->n_leaf = n_leaf;
   t->replicated = replicated;
   t->ncoef = (size_t)(q + 1) * (q + 2) * (q + 3) / 6;
   const size_t ncoef_pad = t->ncoef + (t->ncoef & 1);  // 16-byte rows for TMA / LDS.128
@@ -793,56 +862,12 @@ static int tree_create_impl(tbslas_ctx *ctx, int q, int dof, size_t n_leaf, cons
     tbslas_b200_tree_destroy(t);
     return rc;
   };
-#define TB_TREE_CUDA(call)                                                                   \
-  do {                                                                                       \
-    cudaError_t e_ = (call);                                                                 \
-    if (e_ != cudaSuccess)                                                                   \
-      return bail(fail(ctx, TBSLAS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)));      \
-  } while (0)
-  TB_TREE_CUDA(cudaMalloc(&t->d_key, sizeof(uint64_t) * (n_leaf + 1)));
-  TB_TREE_CUDA(cudaMalloc(&t->d_geom, sizeof(double4) * (n_leaf + 1)));
-  TB_TREE_CUDA(cudaMalloc(&t->d_depth, n_leaf + 1));
-  TB_TREE_CUDA(cudaMalloc(&t->d_box, sizeof(uint4) * (n_leaf + 1)));
-  TB_TREE_CUDA(cudaMemcpy(t->d_box, hb.data(), sizeof(uint4) * (n_leaf + 1), cudaMemcpyHostToDevice));
-  t->boxes_ok = boxes_ok;
-  t->boxes_all = boxes_ok;
-  {  // cell table: depth g with about two cells per leaf, 1 <= g <= 6 (1 MiB)
-    int g = 1;
-    while (g < 6 && ((size_t)1 << (3 * g)) < 2 * n_leaf) g++;
-    const size_t n_cell = (size_t)1 << (3 * g);
-    t->cell_shift = 3 * (kMaxDepth - g);
-    std::vector<uint32_t> cell(n_cell + 2);
-    size_t j = 0;
-    for (size_t c = 0; c < n_cell; c++) {
-      const uint64_t first = (uint64_t)c << t->cell_shift;
-      while (j < n_leaf && hk[j] <= first) j++;
-      cell[c] = (uint32_t)j;
-    }
-    cell[n_cell] = cell[n_cell + 1] = (uint32_t)n_leaf;
-    TB_TREE_CUDA(cudaMalloc(&t->d_cell, sizeof(uint32_t) * cell.size()));
-    TB_TREE_CUDA(cudaMemcpy(t->d_cell, cell.data(), sizeof(uint32_t) * cell.size(), cudaMemcpyHostToDevice));
-  }
-  {
-    uint64_t h = 1469598103934665603ull;  // FNV-1a over the leaf keys and depths
-    for (size_t j = 0; j < n_leaf; j++) {
-      h = (h ^ hk[j]) * 1099511628211ull;
-      h = (h ^ hd[j]) * 1099511628211ull;
-    }
-    t->struct_hash = h;
-    t->global_hash = h;
-  }
-  t->n_leaf_max = n_leaf;
-  TB_TREE_CUDA(cudaMalloc(&t->d_coeff, sizeof(double) * t->stride * (n_leaf + 1)));
-  TB_TREE_CUDA(cudaMemcpy(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice));
-  TB_TREE_CUDA(cudaMemcpy(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice));
-  TB_TREE_CUDA(cudaMemcpy(t->d_depth, hd.data(), n_leaf, cudaMemcpyHostToDevice));
-  TB_TREE_CUDA(cudaMemset(t->d_coeff, 0, sizeof(double) * t->stride * (n_leaf + 1)));
-#undef TB_TREE_CUDA
-  t->splitters.assign(1, n_leaf ? hk[0] : ~0ull);
-  int rc = n_leaf ? tbslas_b200_tree_update_coeff(t, coeff, mem) : TBSLAS_OK;
+  int rc = tree_build_structure(t, hc, hd, true);
+  if (rc != TBSLAS_OK) return bail(rc);
+  rc = n_leaf ? tbslas_b200_tree_update_coeff(t, coeff, mem) : TBSLAS_OK;
   if (rc != TBSLAS_OK) return bail(rc);
   if (ctx->nranks > 1 && !replicated) {
-    rc = comm_tree_splitters(t, n_leaf ? hk[0] : ~0ull);
+    rc = comm_tree_splitters(t, t->first_key);
     if (rc != TBSLAS_OK) return bail(rc);
   }
   *out = t;
@@ -904,6 +929,29 @@ int tbslas_b200_tree_get_coeff(tbslas_tree *t, double *coeff, int mem) {
     TB_CUDA(ctx, cudaMemcpy2DAsync(coeff, t->ncoef * sizeof(double), t->d_coeff, ncoef_pad * sizeof(double),
                                    t->ncoef * sizeof(double), t->n_leaf * t->dof, kind, ctx->stream));
   if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBSLAS_OK;
+}
+
+// Co-partitioning (tbslas::SemiMergeTree / pvfmm RedistNodes, tree_utils.h:609-729): the leaves of a
+// Morton-sharded tree move between ranks so that rank r owns global leaves [new_first[r],
+// new_first[r+1]).  Collective.
+int tbslas_b200_tree_reshard(tbslas_tree *t, const size_t *new_first) {
+  if (!t || !new_first) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = t->ctx;
+  if (t->replicated) return fail(ctx, TBSLAS_ERR_INVALID, "tree_reshard: a replicated tree has no shards");
+  TB_TRY(tree_coeff_ready(t));
+  if (ctx->nranks < 2) {
+    if (new_first[0] != 0 || new_first[1] != t->n_leaf)
+      return fail(ctx, TBSLAS_ERR_INVALID, "tree_reshard: single rank owns [0, %zu)", t->n_leaf);
+    return TBSLAS_OK;
+  }
+  return comm_reshard(t, new_first);
+}
+
+int tbslas_b200_tree_global_range(const tbslas_tree *t, size_t *first, size_t *total) {
+  if (!t) return TBSLAS_ERR_INVALID;
+  if (first) *first = (size_t)t->leaf_offset;
+  if (total) *total = t->n_leaf_global;
   return TBSLAS_OK;
 }
 
@@ -1116,6 +1164,12 @@ int tbslas_b200_set_pt2coeff(tbslas_ctx *ctx, int q, const double *M) {
   return set_pt2coeff(ctx, q, M);
 }
 
+int tbslas_b200_has_pt2coeff(tbslas_ctx *ctx, int q, int *has) {
+  if (!ctx || !has || q < 1 || q > TBSLAS_MAX_CHEB_DEG) return TBSLAS_ERR_INVALID;
+  *has = ctx->pt2coeff[q].d_M != nullptr;
+  return TBSLAS_OK;
+}
+
 int tbslas_b200_tree_set_grid_values(tbslas_tree *t, const double *vals, int point_major, int mem) {
   if (!t || (t->n_leaf && !vals)) return TBSLAS_ERR_INVALID;
   tbslas_ctx *ctx = t->ctx;
@@ -1141,20 +1195,78 @@ int tbslas_b200_semilag_insitu_update(const tbslas_field *f1, const tbslas_field
 }
 
 // ---------------------------------------------------------------- cubic grid
+struct tbslas_grid {
+  tbslas_ctx *ctx = nullptr;
+  int n_reg = 0, dof = 0;
+  double *d_grid = nullptr;  // [dof][n_reg^3], resident
+};
+
+int tbslas_b200_grid_create(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, int mem, tbslas_grid **out) {
+  if (!ctx || !out) return TBSLAS_ERR_INVALID;
+  *out = nullptr;
+  if (n_reg < 4 || dof < 1 || !grid)
+    return fail(ctx, TBSLAS_ERR_INVALID, "grid_create: bad argument (n_reg=%d, dof=%d)", n_reg, dof);
+  tbslas_grid *g = new tbslas_grid();
+  g->ctx = ctx;
+  g->n_reg = n_reg;
+  g->dof = dof;
+  const size_t bytes = sizeof(double) * dof * (size_t)n_reg * n_reg * n_reg;
+  if (cudaMalloc(&g->d_grid, bytes) != cudaSuccess) {
+    delete g;
+    return fail(ctx, TBSLAS_ERR_NOMEM, "grid_create: cudaMalloc(%zu bytes)", bytes);
+  }
+  *out = g;
+  return tbslas_b200_grid_update(g, grid, mem);
+}
+
+int tbslas_b200_grid_update(tbslas_grid *g, const double *grid, int mem) {
+  if (!g || !grid) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = g->ctx;
+  const size_t bytes = sizeof(double) * g->dof * (size_t)g->n_reg * g->n_reg * g->n_reg;
+  StageScope sc(ctx, ST_H2D, (double)bytes, 0);
+  TB_CUDA(ctx, cudaMemcpyAsync(g->d_grid, grid, bytes,
+                               mem == TBSLAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               ctx->stream));
+  if (mem == TBSLAS_MEM_HOST) TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_grid_destroy(tbslas_grid *g) {
+  if (!g) return TBSLAS_ERR_INVALID;
+  cudaStreamSynchronize(g->ctx->stream);
+  cudaFree(g->d_grid);
+  delete g;
+  return TBSLAS_OK;
+}
+
+// fast_interp on a resident grid; host buffers: the queries stream in and the values out in chunks
+// (copy-in, kernel and copy-out of consecutive chunks overlap), only 24 + 8*dof B per query cross PCIe
+int tbslas_b200_grid_eval(tbslas_grid *g, const double *pos, size_t n, double *out, int mem) {
+  if (!g) return TBSLAS_ERR_INVALID;
+  tbslas_ctx *ctx = g->ctx;
+  if (n && (!pos || !out)) return fail(ctx, TBSLAS_ERR_INVALID, "grid_eval: null buffer");
+  if (mem == TBSLAS_MEM_DEVICE) return launch_cubic_grid(ctx, g->d_grid, g->n_reg, g->dof, pos, n, out);
+  PipeSpec sp;
+  sp.h_pos = pos;
+  sp.h_val = out;
+  sp.val_dof = g->dof;
+  return run_host_pipeline(
+      ctx, sp, n, [](PipeBufs &, size_t, size_t) { return (int)TBSLAS_OK; },
+      [&](PipeBufs &B, size_t m, size_t) { return launch_cubic_grid(ctx, g->d_grid, g->n_reg, g->dof, B.pos, m, B.val); });
+}
+
+// one-shot form (the grid travels with the call): tbslas::fast_interp's own signature
 int tbslas_b200_cubic_eval(tbslas_ctx *ctx, const double *grid, int n_reg, int dof, const double *pos,
                            size_t n, double *out, int mem) {
   if (!ctx) return TBSLAS_ERR_INVALID;
   if (n_reg < 4 || dof < 1 || !grid || (n && (!pos || !out)))
     return fail(ctx, TBSLAS_ERR_INVALID, "cubic_eval: bad argument (n_reg=%d, dof=%d)", n_reg, dof);
-  HostIO io{ctx, mem};
-  void *dgrid, *dpos, *dout;
-  TB_TRY(io.h2d(WS_GRID, grid, sizeof(double) * dof * (size_t)n_reg * n_reg * n_reg, &dgrid));
-  TB_TRY(io.h2d(WS_POS_A, pos, sizeof(double) * 3 * n, &dpos));
-  TB_TRY(io.out_buf(WS_VAL_B, out, sizeof(double) * dof * n, &dout));
-  TB_TRY(launch_cubic_grid(ctx, (const double *)dgrid, n_reg, dof, (const double *)dpos, n,
-                           (double *)dout));
-  TB_TRY(io.d2h(out, dout, sizeof(double) * dof * n));
-  return io.finish();
+  if (mem == TBSLAS_MEM_DEVICE) return launch_cubic_grid(ctx, grid, n_reg, dof, pos, n, out);
+  tbslas_grid *g = nullptr;
+  TB_TRY(tbslas_b200_grid_create(ctx, grid, n_reg, dof, mem, &g));
+  const int rc = tbslas_b200_grid_eval(g, pos, n, out, mem);
+  tbslas_b200_grid_destroy(g);
+  return rc;
 }
 
 // ---------------------------------------------------------------- next rows

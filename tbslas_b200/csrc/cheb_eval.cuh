@@ -113,7 +113,9 @@ struct RowPair {
   static __device__ __forceinline__ double coef(const double2 *C2, int i) {
     return (i & 1) ? C2[i >> 1].y : C2[i >> 1].x;
   }
-  static __device__ __forceinline__ void run(const double2 *__restrict__ C2,
+  static __device__ __forceinline__ double coef(const double *C1, int i) { return C1[i]; }
+  template <class CP>
+  static __device__ __forceinline__ void run(CP C2,
                                              const double (&px)[PPT][D],
                                              const double (&py)[PYS ? 1 : PPT][D],
                                              const double *s_py, double (&v)[PPT]) {
@@ -146,7 +148,8 @@ struct RowPair {
 template <int Q, int PPT, bool PYS, bool PAIR, int I, int CI>
 struct ZLevel {
   static constexpr int D = Q + 1;
-  static __device__ __forceinline__ void run(const double2 *__restrict__ C2,
+  template <class CP>
+  static __device__ __forceinline__ void run(CP C2,
                                              const double (&px)[PPT][D],
                                              const double (&py)[PYS ? 1 : PPT][D],
                                              const double *s_py, const double (&zc)[PPT],
@@ -334,6 +337,9 @@ int launch_cheb_eval_q(tbslas_ctx *ctx, const EvalArgs &a) {
 }
 
 // points per thread for each degree (register budget: 2*(Q+1)*PPT doubles of bases)
-constexpr int eval_ppt(int q) { return q <= 9 ? 4 : (q <= 12 ? 3 : 2); }
+#ifndef TB_PPT14
+#define TB_PPT14 2
+#endif
+constexpr int eval_ppt(int q) { return q <= 9 ? 4 : (q <= 12 ? 3 : TB_PPT14); }
 
 }  // namespace tb

@@ -52,12 +52,21 @@ enum {
 // ... and its end live in the two ints that follow the 16 (the block is 8 doubles + 1)
 
 constexpr int kWtThreads = 32;  // one warp per CTA: every address below is CTA-uniform
+#ifndef TB_WT_PAIR
+#define TB_WT_PAIR 0  // 1: rows (i,j) and (i,j+1) contracted together (4 instead of 2 DFMA chains per warp)
+#endif
+#ifndef TB_WT_LDS64
+#define TB_WT_LDS64 0  // 1: coefficients by broadcast LDS.64 instead of LDS.128
+#endif
+#ifndef TB_WT_MINB
+#define TB_WT_MINB 8
+#endif
 
 // Work distribution: tiles are handed out in chunks of at most `chunk` consecutive tiles from a
 // global tile counter (zeroed by the locate launcher), so a warp the scheduler favours simply
 // takes more chunks and all workers finish together.
 template <int Q, int PPT, int EPI>
-__global__ void __launch_bounds__(kWtThreads, 8)
+__global__ void __launch_bounds__(kWtThreads, TB_WT_MINB)
 cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, unsigned chunk) {
   constexpr int D = Q + 1;
   constexpr int TP = 32 * PPT;
@@ -253,11 +262,15 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
     bool last = false;
 #pragma unroll 1
     for (int l = 0; l < p.dof; l++) {
+#if TB_WT_LDS64
+      const double *C2 = s_coef + l * p.ncoef_pad;  // 8-byte alignment only: broadcast LDS.64
+#else
       const double2 *C2 = reinterpret_cast<const double2 *>(s_coef + l * p.ncoef_pad);
+#endif
       double u[PPT], tz0[PPT], tz1[PPT];
 #pragma unroll
       for (int s = 0; s < PPT; s++) u[s] = tz0[s] = tz1[s] = 0.0;
-      ZLevel<Q, PPT, false, false, 0, 0>::run(C2, px, py, nullptr, zc, z0, tz0, tz1, u);
+      ZLevel<Q, PPT, false, TB_WT_PAIR != 0, 0, 0>::run(C2, px, py, nullptr, zc, z0, tz0, tz1, u);
       const unsigned n = (unsigned)s_ctl[CT_N];
       const unsigned cnt0 = ring_cnt(n);
 #pragma unroll

@@ -154,6 +154,9 @@ int comm_tree_splitters(tbslas_tree *t, uint64_t first_key) {
     if (all[W * r + 1] && !all[W * r + 3]) t->boxes_all = false;
   }
   t->global_hash = gh;
+  t->rank_first.assign(np + 1, 0);
+  for (int r = 0; r < np; r++) t->rank_first[r + 1] = t->rank_first[r] + (size_t)all[W * r + 1];
+  t->n_leaf_global = t->rank_first[np];
   // a rank without leaves owns the empty range: give it the next owner's first key so the
   // "last rank whose splitter <= key" rule never selects it
   for (int r = np - 1; r >= 0; r--)
@@ -171,6 +174,89 @@ int comm_tree_splitters(tbslas_tree *t, uint64_t first_key) {
   TB_CUDA(ctx, cudaMemcpy(t->d_splitters, t->splitters.data(), sizeof(uint64_t) * np,
                           cudaMemcpyHostToDevice));
   return TBSLAS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// co-partitioning: leaves move between ranks (tbslas::SemiMergeTree -> pvfmm RedistNodes,
+// tree_utils.h:609-729: the reference recomputes break points and MOVES the nodes)
+// ---------------------------------------------------------------------------
+// Rank r ends up with global leaves [new_first[r], new_first[r+1]).  Old and new ranges are both
+// contiguous in the global Morton order, so what rank a sends to rank b is one contiguous run:
+// geometry (32 B), depth (1 B) and the coefficient block (stride doubles) of every leaf in
+// [max(old_a, new_b), min(old_a', new_b')).  Grouped ncclSend/ncclRecv straight between the trees'
+// device arrays; the derived structures (keys, boxes, cell table, hashes, split keys) are rebuilt
+// from the received leaf list exactly as tree_create builds them.
+int comm_reshard(tbslas_tree *t, const size_t *new_first) {
+  tbslas_ctx *ctx = t->ctx;
+  const int np = ctx->nranks, me = ctx->rank;
+  if ((int)t->rank_first.size() != np + 1) return fail(ctx, TBSLAS_ERR_INVALID, "tree_reshard: not a sharded tree");
+  const std::vector<size_t> &of = t->rank_first;
+  if (new_first[0] != 0 || new_first[np] != of[np])
+    return fail(ctx, TBSLAS_ERR_INVALID, "tree_reshard: new ranges must cover [0, %zu)", of[np]);
+  for (int r = 0; r < np; r++)
+    if (new_first[r] > new_first[r + 1]) return fail(ctx, TBSLAS_ERR_INVALID, "tree_reshard: ranges must ascend");
+  const size_t n_new = new_first[me + 1] - new_first[me], stride = t->stride;
+  double4 *g_new = nullptr;
+  uint8_t *d_new = nullptr;
+  double *c_new = nullptr;
+  TB_CUDA(ctx, cudaMalloc(&g_new, sizeof(double4) * (n_new + 1)));
+  TB_CUDA(ctx, cudaMalloc(&d_new, n_new + 1));
+  TB_CUDA(ctx, cudaMalloc(&c_new, sizeof(double) * stride * (n_new + 1)));
+  TB_CUDA(ctx, cudaMemsetAsync(c_new + stride * n_new, 0, sizeof(double) * stride, ctx->stream));  // null leaf
+  auto overlap = [](size_t a0, size_t a1, size_t b0, size_t b1, size_t *lo, size_t *hi) {
+    *lo = a0 > b0 ? a0 : b0;
+    *hi = a1 < b1 ? a1 : b1;
+    return *lo < *hi;
+  };
+  TB_NCCL(ctx, g_nccl.GroupStart());
+  for (int r = 0; r < np; r++) {
+    size_t lo, hi;
+    if (overlap(of[me], of[me + 1], new_first[r], new_first[r + 1], &lo, &hi)) {  // mine -> r
+      const size_t s = lo - of[me], m = hi - lo;
+      if (r == me) {
+        const size_t d = lo - new_first[me];
+        TB_CUDA(ctx, cudaMemcpyAsync(g_new + d, t->d_geom + s, sizeof(double4) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+        TB_CUDA(ctx, cudaMemcpyAsync(d_new + d, t->d_depth + s, m, cudaMemcpyDeviceToDevice, ctx->stream));
+        TB_CUDA(ctx, cudaMemcpyAsync(c_new + d * stride, t->d_coeff + s * stride, sizeof(double) * stride * m,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+      } else {
+        TB_NCCL(ctx, g_nccl.Send(t->d_geom + s, sizeof(double4) * m, ncclUint8, r, comm_of(ctx), ctx->stream));
+        TB_NCCL(ctx, g_nccl.Send(t->d_depth + s, m, ncclUint8, r, comm_of(ctx), ctx->stream));
+        TB_NCCL(ctx, g_nccl.Send(t->d_coeff + s * stride, sizeof(double) * stride * m, ncclUint8, r, comm_of(ctx),
+                                 ctx->stream));
+      }
+    }
+    if (r != me && overlap(of[r], of[r + 1], new_first[me], new_first[me + 1], &lo, &hi)) {  // r's -> me
+      const size_t d = lo - new_first[me], m = hi - lo;
+      TB_NCCL(ctx, g_nccl.Recv(g_new + d, sizeof(double4) * m, ncclUint8, r, comm_of(ctx), ctx->stream));
+      TB_NCCL(ctx, g_nccl.Recv(d_new + d, m, ncclUint8, r, comm_of(ctx), ctx->stream));
+      TB_NCCL(ctx, g_nccl.Recv(c_new + d * stride, sizeof(double) * stride * m, ncclUint8, r, comm_of(ctx),
+                               ctx->stream));
+    }
+  }
+  TB_NCCL(ctx, g_nccl.GroupEnd());
+  // the new leaf list on the host -> derived structures
+  std::vector<double4> hg(n_new);
+  std::vector<uint8_t> hd(n_new);
+  TB_CUDA(ctx, cudaMemcpyAsync(hg.data(), g_new, sizeof(double4) * n_new, cudaMemcpyDeviceToHost, ctx->stream));
+  TB_CUDA(ctx, cudaMemcpyAsync(hd.data(), d_new, n_new, cudaMemcpyDeviceToHost, ctx->stream));
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(g_new);
+  cudaFree(d_new);
+  std::vector<double> hc(3 * n_new);
+  for (size_t j = 0; j < n_new; j++) {
+    hc[3 * j] = hg[j].x;
+    hc[3 * j + 1] = hg[j].y;
+    hc[3 * j + 2] = hg[j].z;
+  }
+  const int rc = tree_build_structure(t, hc, hd, false);
+  if (rc != TBSLAS_OK) {
+    cudaFree(c_new);
+    return rc;
+  }
+  cudaFree(t->d_coeff);
+  t->d_coeff = c_new;
+  return comm_tree_splitters(t, t->first_key);
 }
 
 // ---------------------------------------------------------------------------

@@ -181,6 +181,9 @@ struct tbslas_tree {
   cudaEvent_t ev_coeff = nullptr;
   bool coeff_pending = false;
   size_t n_leaf_max = 0;       // most local leaves any rank holds (== n_leaf in a single-rank context)
+  size_t n_leaf_global = 0;    // leaves of all ranks
+  std::vector<size_t> rank_first;  // [nranks+1] global index of every rank's first leaf (sharded trees)
+  uint64_t first_key = ~0ull;  // key of local leaf 0 (~0: no leaves)
   bool replicated = false;  // multi-rank context, but every rank holds the WHOLE tree: no exchange
   // Morton-range sharding (nranks > 1)
   long long leaf_offset = 0;                 // global index of local leaf 0
@@ -192,7 +195,9 @@ namespace tb {
 
 int fail(tbslas_ctx *ctx, int code, const char *fmt, ...);
 int ws_get(tbslas_ctx *ctx, Slot s, size_t bytes, void **out);
-int tree_coeff_ready(const tbslas_tree *t);  // orders the context's stream after a pending async upload
+int tree_coeff_ready(const tbslas_tree *t);
+int tree_build_structure(tbslas_tree *t, const std::vector<double> &hc, const std::vector<uint8_t> &hd,
+                         bool alloc_coeff);  // orders the context's stream after a pending async upload
 
 struct StageScope {  // CUDA-event bracket of one stage on the context's stream
   tbslas_ctx *ctx;

@@ -184,6 +184,56 @@ def main():
 
         all_checks += [(tag + n_, ok_) for n_, ok_ in checks]
     checks = all_checks
+
+    # (6) co-partitioning (row f4; tbslas::SemiMergeTree / RedistNodes, tree_utils.h:609-729): re-balance
+    # the advected tree by the points each leaf received in its last evaluation, MOVE the leaves
+    # between the GPUs, re-shard the velocity trees with the new split keys -- and every result is
+    # still bit-identical to the single-GPU path.
+    ctx.comm_set_exchange(modes[0])
+    f = api.NodeFieldFunctor(tcon)
+    skew = np.concatenate([np.random.default_rng(7 + rank).uniform(0, 1, size=(30000, 3)) ** 3, pts[:5000]])
+    f(skew.copy(), bc=0)
+    mine = tcon.last_point_counts().astype(np.float64)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    weight = np.concatenate(gathered) + 1.0
+    assert weight.shape[0] == con.n_leaf
+    new_first = api.partition_leaves_weighted(weight, world)
+    moved = int(np.abs(new_first - first).sum())
+    tcon.reshard(new_first)
+    lo_l, hi_l = int(new_first[rank]), int(new_first[rank + 1])
+    checks.append(("reshard: leaves moved", world == 1 or moved > 0))
+    checks.append(("reshard: new local range", tcon.n_leaf == hi_l - lo_l and tcon.global_range() == (lo_l, con.n_leaf)))
+    new_split = con.keys()[np.minimum(new_first[:-1], con.n_leaf - 1)]
+    for i, v in enumerate(vels):
+        own = workloads.owner_of_keys(v.keys(), np.asarray(new_split, dtype=np.uint64))
+        vf = np.searchsorted(own, np.arange(world + 1), side="left")
+        tvel[i].reshard(vf)
+
+    def same2(name, a, b):
+        ok = np.array_equal(a, b)
+        checks.append((name, ok))
+        if not ok:
+            print("[rank %d] MISMATCH %s" % (rank, name), flush=True)
+    for bc in (0, 1):
+        va, la = api.NodeFieldFunctor(tcon).eval_with_leaf(pts.copy(), bc)
+        vb, lb = api.NodeFieldFunctor(scon).eval_with_leaf(pts.copy(), bc)
+        same2("after reshard: eval values bc%d" % bc, va, vb)
+        same2("after reshard: leaf ids bc%d" % bc, la, lb)
+        same2("after reshard: dof3 bc%d" % bc, api.NodeFieldFunctor(tvel[1])(pts.copy(), bc=bc),
+              api.NodeFieldFunctor(svel[1])(pts.copy(), bc=bc))
+    con_n = con.shard(lo_l, hi_l)
+    same2("after reshard: coefficients moved intact", tcon.coefficients(), con_n.coeff)
+    arr_n = ftm.grid_points(con_n.coord, con_n.depth, q)
+    same2("after reshard: semilag on the new shard's arrival points",
+          api.SolveSemilagRK2(api.FieldSetFunctor(tvel, times), api.NodeFieldFunctor(tcon), arr_n, 3, 0.05, 1, 1),
+          api.SolveSemilagRK2(api.FieldSetFunctor(svel, times), api.NodeFieldFunctor(scon), arr_n, 3, 0.05, 1, 1))
+    ctx.set_tensor_grid("always")
+    solo.set_tensor_grid("always")
+    Pn = (q + 1) ** 3
+    a = api.SolveSemilagInSitu(api.NodeFieldFunctor(rtree), tcon, 2, 0.05, 1, 0)
+    b = api.SolveSemilagInSitu(api.NodeFieldFunctor(svel[1]), scon, 2, 0.05, 1, 0)
+    same2("after reshard: tree-level step", a, b[lo_l * Pn:hi_l * Pn])
     ok = all(c[1] for c in checks)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

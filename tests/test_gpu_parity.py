@@ -315,6 +315,45 @@ def test_gpu_traj_and_semilag_vs_oracle(ctx, port, bc, nrk):
     assert rel_err(s, so) < STEP_TOL
 
 
+@pytest.mark.parametrize("bc", [0, 1])
+def test_gpu_ns_call_pattern_vs_oracle(ctx, port, bc):
+    """The Navier-Stokes stepper's use of the path (tree_ns.h:466-518): the advected field is the dof-3
+    velocity itself.  Two backward trajectories from the same arrival points -- [t, t-dt] with stage 1
+    = v^n and stage 2 = the extrapolation 1.5 v^n - 0.5 v^{n-1}; [t, t-2dt] with stage 1 = v^{n-1} and
+    stage 2 = v^n -- the velocity trees sampled at the two sets of departure points, combined
+    2/dt*c - 0.5/dt*p, transposed point-major -> dof-major and refitted.  Stage by stage against the
+    oracle: departure points 1e-12, values at equal points 1e-12, refit 1e-12 of the coefficient scale."""
+    api = _api()
+    q, dt, nrk, ts = 6, 0.02, 2, 3
+    coord, dd = adaptive_leaves(4, 2)
+    fp_ = ftm.fit(coord, dd, q, 3, lambda p: 0.9 * ftm.vel_rotation(p) + 0.2 * ftm.vel_taylor_green(p))
+    fc_ = ftm.fit(coord, dd, q, 3, lambda p: 1.0 * ftm.vel_rotation(p) + 0.25 * ftm.vel_taylor_green(p))
+    tp, tc, tn = ctx.tree(fp_), ctx.tree(fc_), ctx.tree(fc_)
+    fp, fc, fe = api.NodeFieldFunctor(tp), api.NodeFieldFunctor(tc), api.FieldExtrapFunctor(tp, tc)
+    hp, hc = port.tree_create(fp_), port.tree_create(fc_)
+    arr = tn.collect_grid_points()
+    tcur = ts * dt
+    d1 = api.ComputeTrajRK2(fc, arr, tcur, tcur - dt, nrk, bc, extrap_fn=fe)
+    c = fc(d1.copy(), bc=bc)
+    d2 = api.ComputeTrajRK2(fp, arr, tcur, tcur - 2 * dt, nrk, bc, extrap_fn=fc)
+    p = fp(d2.copy(), bc=bc)
+    assert np.abs(d1 - port.traj_rk2((hp, hc), arr, tcur, tcur - dt, nrk, bc, kind="extrap")).max() < RTOL
+    assert np.abs(d2 - port.traj_rk2((hp, hc), arr, tcur, tcur - 2 * dt, nrk, bc, kind="pair")).max() < RTOL
+    assert rel_err(c, port.eval_tree(hc, 3, d1, bc, want_leaf=False)[0]) < RTOL
+    assert rel_err(p, port.eval_tree(hp, 3, d2, bc, want_leaf=False)[0]) < RTOL
+    val = (2.0 / dt) * c + (-0.5 / dt) * p                       # [L*P, 3] point-major
+    P = (q + 1) ** 3
+    ml = np.ascontiguousarray(val.reshape(-1, P, 3).transpose(0, 2, 1))  # [L, 3, P] (tree_ns.h:502-513)
+    ctx.set_pt2coeff(q)
+    tn.set_grid_values(ml, point_major=False)
+    want = np.einsum("ldp,pn->ldn", ml, ftm.pt2coeff(q))
+    assert np.abs(tn.coefficients() - want).max() < 1e-12 * np.abs(want).max()
+    tn.set_grid_values(val, point_major=True)                    # the library's own transpose
+    assert np.abs(tn.coefficients() - want).max() < 1e-12 * np.abs(want).max()
+    for t in (tp, tc, tn):
+        t.destroy()
+
+
 def test_gpu_device_resident_buffers(ctx, port):
     """Same results when the caller's buffers are device pointers (torch CUDA tensors)."""
     import torch
@@ -517,6 +556,41 @@ def test_gpu_cubic_grid_vs_oracle(ctx, port):
         pts[:64] = rng.integers(0, n_reg, size=(64, 3)) / (n_reg - 1.0)
         assert np.array_equal(ctx.fast_interp(grid, dof, n_reg, pts),
                               port.fast_interp(grid, dof, n_reg, pts))
+
+
+def test_gpu_resident_cubic_grid_handle(ctx, port):
+    """tbslas_b200_grid_create/eval/update/destroy: the same bits as the one-shot call, host and
+    device buffers, chunked host pipeline included."""
+    import torch
+    rng = np.random.default_rng(18)
+    n_reg, dof = 21, 3
+    grid = rng.standard_normal((dof, n_reg, n_reg, n_reg))
+    pts = rng.uniform(-0.02, 1.02, size=(70001, 3))
+    want = port.fast_interp(grid, dof, n_reg, pts)
+    g = ctx.grid(grid, dof, n_reg)
+    assert np.array_equal(g(pts), want)
+    ctx.set_host_chunks(5)
+    assert np.array_equal(g(pts), want)
+    ctx.set_host_chunks(0)
+    ctx.set_stream(torch.cuda.current_stream())
+    dv = g(torch.from_numpy(pts).cuda())
+    torch.cuda.synchronize()
+    ctx.set_stream(None)
+    assert np.array_equal(dv.cpu().numpy(), want)
+    grid2 = 2.0 * grid
+    g.update(grid2)
+    assert np.array_equal(g(pts), port.fast_interp(grid2, dof, n_reg, pts))
+    g.destroy()
+
+
+def test_gpu_reshard_single_rank_is_a_checked_no_op(ctx):
+    coord, dd = ftm.uniform_leaves(2)
+    t = ctx.tree(ftm.random_tree(coord, dd, 4, 1, seed=1))
+    t.reshard([0, 64])
+    assert t.global_range() == (0, 64)
+    with pytest.raises(Exception):
+        t.reshard([0, 63])
+    t.destroy()
 
 
 # ---------------------------------------------------------------- size-independent properties
