@@ -649,15 +649,16 @@ int tree_build_structure(tbslas_tree *t, const std::vector<double> &hc, const st
   TB_CUDA(ctx, cudaMalloc(&t->d_geom, sizeof(double4) * (n_leaf + 1)));
   TB_CUDA(ctx, cudaMalloc(&t->d_depth, n_leaf + 1));
   TB_CUDA(ctx, cudaMalloc(&t->d_box, sizeof(uint4) * (n_leaf + 1)));
-  TB_CUDA(ctx, cudaMemcpy(t->d_box, hb.data(), sizeof(uint4) * (n_leaf + 1), cudaMemcpyHostToDevice));
+  TB_CUDA(ctx, cudaMemcpyAsync(t->d_box, hb.data(), sizeof(uint4) * (n_leaf + 1), cudaMemcpyHostToDevice, ctx->stream));
   t->boxes_ok = boxes_ok;
   t->boxes_all = boxes_ok;
+  std::vector<uint32_t> cell;
   {  // cell table: depth g with about two cells per leaf, 1 <= g <= 6 (1 MiB)
     int g = 1;
     while (g < 6 && ((size_t)1 << (3 * g)) < 2 * n_leaf) g++;
     const size_t n_cell = (size_t)1 << (3 * g);
     t->cell_shift = 3 * (kMaxDepth - g);
-    std::vector<uint32_t> cell(n_cell + 2);
+    cell.assign(n_cell + 2, 0u);
     size_t j = 0;
     for (size_t c = 0; c < n_cell; c++) {
       const uint64_t first = (uint64_t)c << t->cell_shift;
@@ -666,7 +667,7 @@ int tree_build_structure(tbslas_tree *t, const std::vector<double> &hc, const st
     }
     cell[n_cell] = cell[n_cell + 1] = (uint32_t)n_leaf;
     TB_CUDA(ctx, cudaMalloc(&t->d_cell, sizeof(uint32_t) * cell.size()));
-    TB_CUDA(ctx, cudaMemcpy(t->d_cell, cell.data(), sizeof(uint32_t) * cell.size(), cudaMemcpyHostToDevice));
+    TB_CUDA(ctx, cudaMemcpyAsync(t->d_cell, cell.data(), sizeof(uint32_t) * cell.size(), cudaMemcpyHostToDevice, ctx->stream));
   }
   {
     uint64_t h = 1469598103934665603ull;  // FNV-1a over the leaf keys and depths
@@ -681,17 +682,21 @@ int tree_build_structure(tbslas_tree *t, const std::vector<double> &hc, const st
   t->n_leaf_global = n_leaf;
   t->leaf_offset = 0;
   t->rank_first.assign({(size_t)0, n_leaf});
-  TB_CUDA(ctx, cudaMemcpy(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice));
-  TB_CUDA(ctx, cudaMemcpy(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice));
-  TB_CUDA(ctx, cudaMemcpy(t->d_depth, hd.data(), n_leaf, cudaMemcpyHostToDevice));
+  TB_CUDA(ctx, cudaMemcpyAsync(t->d_key, hk.data(), sizeof(uint64_t) * n_leaf, cudaMemcpyHostToDevice, ctx->stream));
+  TB_CUDA(ctx, cudaMemcpyAsync(t->d_geom, hg.data(), sizeof(double4) * (n_leaf + 1), cudaMemcpyHostToDevice, ctx->stream));
+  TB_CUDA(ctx, cudaMemcpyAsync(t->d_depth, hd.data(), n_leaf, cudaMemcpyHostToDevice, ctx->stream));
   if (alloc_coeff) {
     cudaFree(t->d_coeff);
     t->d_coeff = nullptr;
     TB_CUDA(ctx, cudaMalloc(&t->d_coeff, sizeof(double) * t->stride * (n_leaf + 1)));
-    TB_CUDA(ctx, cudaMemset(t->d_coeff, 0, sizeof(double) * t->stride * (n_leaf + 1)));
+    // on the context's stream: the coefficient upload that follows must not overtake it
+    TB_CUDA(ctx, cudaMemsetAsync(t->d_coeff, 0, sizeof(double) * t->stride * (n_leaf + 1), ctx->stream));
   }
   t->first_key = n_leaf ? hk[0] : ~0ull;
   t->splitters.assign(1, t->first_key);
+  // everything above went through the context's stream (a copy on the legacy default stream is not
+  // ordered with a non-blocking stream); the host vectors must outlive the copies
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TBSLAS_OK;
 }
 

@@ -171,8 +171,9 @@ int comm_tree_splitters(tbslas_tree *t, uint64_t first_key) {
     if (want <= 0x7fffffffu) TB_TRY(px_grow(ctx, want));
   }
   if (!t->d_splitters) TB_CUDA(ctx, cudaMalloc(&t->d_splitters, sizeof(uint64_t) * kMaxRanks));
-  TB_CUDA(ctx, cudaMemcpy(t->d_splitters, t->splitters.data(), sizeof(uint64_t) * np,
-                          cudaMemcpyHostToDevice));
+  TB_CUDA(ctx, cudaMemcpyAsync(t->d_splitters, t->splitters.data(), sizeof(uint64_t) * np, cudaMemcpyHostToDevice,
+                               ctx->stream));
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TBSLAS_OK;
 }
 
@@ -590,7 +591,8 @@ int px_setup(tbslas_ctx *ctx, size_t cap) {
   PxPeers peers;
   memset(&peers, 0, sizeof(peers));
   for (int r = 0; r < np; r++) peers.base[r] = x.peer_base[r];
-  TB_CUDA(ctx, cudaMemcpy(x.d_peers, &peers, sizeof(peers), cudaMemcpyHostToDevice));
+  TB_CUDA(ctx, cudaMemcpyAsync(x.d_peers, &peers, sizeof(peers), cudaMemcpyHostToDevice, ctx->stream));
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   x.px_ok = true;
   return TBSLAS_OK;
 }

@@ -155,7 +155,9 @@ int set_pt2coeff(tbslas_ctx *ctx, int q, const double *M_host) {
     m.d_M = nullptr;
   }
   TB_CUDA(ctx, cudaMalloc(&m.d_M, padded.size() * sizeof(double)));
-  TB_CUDA(ctx, cudaMemcpy(m.d_M, padded.data(), padded.size() * sizeof(double), cudaMemcpyHostToDevice));
+  TB_CUDA(ctx, cudaMemcpyAsync(m.d_M, padded.data(), padded.size() * sizeof(double), cudaMemcpyHostToDevice,
+                               ctx->stream));
+  TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TBSLAS_OK;
 }
 
