@@ -322,6 +322,11 @@ int tbslas_b200_profile_enable(tbslas_ctx *ctx, int on);
 int tbslas_b200_profile_reset(tbslas_ctx *ctx);
 int tbslas_b200_profile_num_stages(void);
 const char *tbslas_b200_profile_stage_name(int stage);
+/* The pvfmm::Profile::Tic tag(s) of the reference's EvalTree that the stage stands for ("" if the
+ * reference has none), e.g. Locate -> "LclHQSort" (tree_functor.h:463), ChebEval ->
+ * "InEvaluation/OutEvaluation" (:674, :585), Exchange -> "OutScatterForward/OutScatterReverse"
+ * (:573, :593).  Every stage is also an NVTX range named "<stage> (<tag>)". */
+const char *tbslas_b200_profile_reference_tag(int stage);
 int tbslas_b200_profile_get(tbslas_ctx *ctx, int stage, double *ms, long long *launches,
                             double *units);
 /* Total kernels launched by this context since init (the bench's gpu_launches). */

@@ -34,7 +34,7 @@ SYMBOLS = [
     "tbslas_b200_new_nodes", "tbslas_b200_point_key", "tbslas_b200_owner_of_key",
     "tbslas_b200_partition_leaves", "tbslas_b200_partition_leaves_weighted",
     "tbslas_b200_tree_reshard", "tbslas_b200_tree_global_range", "tbslas_b200_tree_last_point_counts", "tbslas_b200_tree_tail_norm", "tbslas_b200_profile_enable", "tbslas_b200_profile_reset",
-    "tbslas_b200_profile_num_stages", "tbslas_b200_profile_stage_name",
+    "tbslas_b200_profile_num_stages", "tbslas_b200_profile_stage_name", "tbslas_b200_profile_reference_tag",
     "tbslas_b200_profile_get", "tbslas_b200_kernel_launches", "tbslas_b200_fp64_peak",
 ]
 
@@ -131,6 +131,8 @@ def load() -> C.CDLL:
     L.tbslas_b200_profile_reset.argtypes = [vp]
     L.tbslas_b200_profile_stage_name.argtypes = [C.c_int]
     L.tbslas_b200_profile_stage_name.restype = C.c_char_p
+    L.tbslas_b200_profile_reference_tag.argtypes = [C.c_int]
+    L.tbslas_b200_profile_reference_tag.restype = C.c_char_p
     L.tbslas_b200_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
                                           C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     L.tbslas_b200_kernel_launches.argtypes = [vp]

@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a tool is attached
+
 #include "common.cuh"
 #include "keys.cuh"
 
@@ -45,7 +47,30 @@ int ws_get(tbslas_ctx *ctx, Slot s, size_t bytes, void **out) {
   return TBSLAS_OK;
 }
 
+// The active pvfmm::Profile::Tic tags of the reference's EvalTree (tree_functor.h) that each stage
+// stands for; NVTX ranges carry "<stage> (<tag>)" so a timeline reads like the reference's profile.
+static const char *kStageRefTags[ST_COUNT] = {
+    "",                                   // H2D
+    "",                                   // D2H
+    "LclHQSort",                          // Locate     :463 (sort of the (key,index) pairs + part_indx)
+    "LclHQSort",                          // Bin        :463 (the sort's permutation)
+    "InEvaluation/OutEvaluation",         // ChebEval   :674 / :585
+    "",                                   // Combine    (tree_set_functor.h:66-72, no tag)
+    "",                                   // CubicGrid  (fast_interp, no tag)
+    "OutScatterIndex",                    // Pack       :568
+    "OutScatterForward/OutScatterReverse",// Exchange   :573 / :593
+    "OutScatterReverse",                  // Unpack     :593-619
+    "",                                   // GridPoints (CollectChebTreeGridPoints, no tag)
+    "",                                   // Refit      (SetTreeGridValues, no tag)
+    "InEvaluation",                       // TensorGrid (first velocity evaluation of a tree-level step)
+};
+static const char *kStageNvtx[ST_COUNT] = {
+    "H2D", "D2H", "Locate (LclHQSort)", "Bin (LclHQSort)", "ChebEval (In/OutEvaluation)", "Combine", "CubicGrid",
+    "Pack (OutScatterIndex)", "Exchange (OutScatterForward/Reverse)", "Unpack (OutScatterReverse)", "GridPoints",
+    "Refit (SetTreeGridValues)", "TensorGrid (InEvaluation)"};
+
 StageScope::StageScope(tbslas_ctx *c, int stage, double units, int n_launch) : ctx(c) {
+  nvtxRangePushA(kStageNvtx[stage]);
   c->launches += n_launch;
   c->acc_launch[stage] += n_launch;
   c->acc_units[stage] += units;
@@ -67,6 +92,7 @@ StageScope::StageScope(tbslas_ctx *c, int stage, double units, int n_launch) : c
 }
 StageScope::~StageScope() {
   if (idx >= 0) cudaEventRecord(ctx->recs[idx].b, ctx->stream);
+  nvtxRangePop();
 }
 
 static int prof_collect(tbslas_ctx *ctx) {
@@ -1384,6 +1410,9 @@ int tbslas_b200_profile_reset(tbslas_ctx *ctx) {
 int tbslas_b200_profile_num_stages(void) { return ST_COUNT; }
 const char *tbslas_b200_profile_stage_name(int s) {
   return (s >= 0 && s < ST_COUNT) ? kStageNames[s] : "";
+}
+const char *tbslas_b200_profile_reference_tag(int s) {
+  return (s >= 0 && s < ST_COUNT) ? kStageRefTags[s] : "";
 }
 int tbslas_b200_profile_get(tbslas_ctx *ctx, int stage, double *ms, long long *launches, double *units) {
   if (!ctx || stage < 0 || stage >= ST_COUNT) return TBSLAS_ERR_INVALID;
