@@ -543,6 +543,29 @@ def run_b200(args):
     tree_s = allmax((time.perf_counter() - t0) / e2e_steps)
     checksum_tree = float(np_vals.sum())
     h_sum, h_bits = checksums(torch.from_numpy(np_vals))
+
+    # ---- the whole tbslas::SolveSemilagInSitu through host memory: what the C++ drop-in adaptor does
+    # per step -- coefficients up, arrival points + RK2 + scalar + refit on the device, the NEW
+    # COEFFICIENTS down.  Only 2 x 8*Ncoef/P = 3.2 B per point cross PCIe instead of 8 B of values.
+    scratch2 = ctx.tree(con_local)
+    h_cout = torch.empty((con_local.n_leaf, 1, nc), dtype=torch.float64, pin_memory=True)
+    np_cout = h_cout.numpy()
+
+    def step_tree_coeff():
+        scratch2.update_coeff(np_coef, wait=False)
+        api.SolveSemilagInSituUpdate(vel_f, scratch2, 1, wl.dt, 1, wl.bc)
+        ctx.check(ctx.lib.tbslas_b200_tree_get_coeff(scratch2.h, np_cout.ctypes.data, 0))  # returns when landed
+
+    for _ in range(2):
+        step_tree_coeff()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_tree_coeff()
+    barrier()
+    coef_s = allmax((time.perf_counter() - t0) / e2e_steps)
+    coef_sum = float(np_cout.sum())
+    scratch2.destroy()
     exch_mode = ctx.comm_exchange_mode() if world > 1 else ("none", 0)
 
     if rank != 0:
@@ -641,6 +664,14 @@ def run_b200(args):
                         "host memory (under the velocity evaluations), arrival points generated in HBM, advected "
                         "grid values down to pinned host memory; leaf chunks pipelined (D2H of chunk c-1 under "
                         "the kernels of chunk c); wall clock over all timed steps",
+                "coefficients_out": {
+                    "value": n_total / coef_s, "unit": "points/s", "ms_per_step": coef_s * 1e3,
+                    "h2d_bytes_per_step": int(con_local.n_leaf * nc * 8),
+                    "d2h_bytes_per_step": int(con_local.n_leaf * nc * 8), "checksum": coef_sum,
+                    "what": "the whole tbslas::SolveSemilagInSitu (tree_semilag.h:92-135) through host memory, as "
+                            "the C++ drop-in adaptor runs it: tbslas_b200_tree_update_coeff_async + "
+                            "tbslas_b200_semilag_insitu_update (values refitted on the device, FP64 tensor-core "
+                            "GEMM) + tbslas_b200_tree_get_coeff"},
                 "point_array_call": {
                     "value": n_total / e2e_s, "unit": "points/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(n_local * 24), "d2h_bytes_per_step": int(n_local * 8),

@@ -519,16 +519,22 @@ constexpr double kChunkRatio = 0.62;
 static double chunk_cum(int K, int c) {  // fraction of the units in chunks 0..c-1
   return (1.0 - pow(kChunkRatio, c)) / (1.0 - pow(kChunkRatio, K));
 }
-static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input, size_t n_collective) {
+// Four or more GPUs of one host share its PCIe root complexes: measured 21.8 GB/s per GPU with four
+// copying at once against 53 GB/s for one alone (bench line, e2e.pcie_d2h_GBps_slowest_rank).  The
+// copy-out is then the bottleneck of a tree-level call, nothing hides it, and what matters is that
+// it starts early: uniform chunks of about 4 Mi points.
+static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input, size_t n_collective, bool *geometric) {
+  *geometric = false;
   if (ctx->host_chunks > 0) return ctx->host_chunks;
   if (ctx->nranks > 1) {
     if (!n_collective) return 8;
     n = n_collective;
   }
-  if (has_input) {
+  if (has_input || ctx->nranks >= 4) {
     const size_t per = (size_t)4 << 20, k = (n + per / 2) / per;
     return (int)(k < 1 ? 1 : (k > 16 ? 16 : k));
   }
+  *geometric = true;
   int k = 1;  // fewest chunks whose last one holds at most 8 Mi points
   while (k < 12 && (double)n * (1.0 - chunk_cum(k, k - 1)) > (double)((size_t)8 << 20)) k++;
   return k;
@@ -546,10 +552,10 @@ static size_t chunk_first_unit(size_t U, int K, int c, bool geometric) {
 template <class FA, class FB>
 static int run_host_pipeline(tbslas_ctx *ctx, const PipeSpec &sp, size_t n, FA phase_a, FB phase_b) {
   const bool has_input = sp.h_pos != nullptr;
-  const int K = pipe_chunks(ctx, n, has_input, sp.n_collective);
+  bool halving = false;  // (chunks of geometrically decreasing size)
+  const int K = pipe_chunks(ctx, n, has_input, sp.n_collective, &halving);
   const size_t unit = sp.unit ? sp.unit : 1;
   const size_t U = (n + unit - 1) / unit;
-  const bool halving = !has_input && ctx->host_chunks == 0;
   size_t chunk = 0;  // largest chunk, in points
   for (int c = 0; c < K; c++) {
     const size_t u = chunk_first_unit(U, K, c + 1, halving) - chunk_first_unit(U, K, c, halving);
