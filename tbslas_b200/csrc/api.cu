@@ -519,10 +519,11 @@ constexpr double kChunkRatio = 0.62;
 static double chunk_cum(int K, int c) {  // fraction of the units in chunks 0..c-1
   return (1.0 - pow(kChunkRatio, c)) / (1.0 - pow(kChunkRatio, K));
 }
-// Four or more GPUs of one host share its PCIe root complexes: measured 21.8 GB/s per GPU with four
-// copying at once against 53 GB/s for one alone (bench line, e2e.pcie_d2h_GBps_slowest_rank).  The
-// copy-out is then the bottleneck of a tree-level call, nothing hides it, and what matters is that
-// it starts early: uniform chunks of about 4 Mi points.
+// (Four or more GPUs of one host share its PCIe root complexes: measured 21.8-26 GB/s per GPU with
+// four copying at once against 53 GB/s for one alone, bench line e2e.pcie_d2h_GBps_slowest_rank.  The
+// copy-out is then the bottleneck whatever the schedule; 16 uniform chunks were measured there and
+// lost to the geometric schedule, 43.1 against 37.2 ms per step, because every chunk of a multi-rank
+// call is a collective evaluation.)
 static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input, size_t n_collective, bool *geometric) {
   *geometric = false;
   if (ctx->host_chunks > 0) return ctx->host_chunks;
@@ -530,7 +531,7 @@ static int pipe_chunks(tbslas_ctx *ctx, size_t n, bool has_input, size_t n_colle
     if (!n_collective) return 8;
     n = n_collective;
   }
-  if (has_input || ctx->nranks >= 4) {
+  if (has_input) {
     const size_t per = (size_t)4 << 20, k = (n + per / 2) / per;
     return (int)(k < 1 ? 1 : (k > 16 ? 16 : k));
   }
