@@ -267,6 +267,8 @@ def run_b200(args):
     wl = workloads.make(args.workload, dev, args.scale)
     ctx = api.Context(local)
     ctx.set_stream(torch.cuda.current_stream())
+    if args.tensor_grid:
+        ctx.set_tensor_grid("always" if args.tensor_grid == "always" else False)
     if world > 1:
         ctx.comm_init_torch()
         if args.exchange:
@@ -850,6 +852,9 @@ def main():
     ap.add_argument("--parity-points", type=int, default=2048, help="oracle sample per rank")
     ap.add_argument("--no-sharded", action="store_true",
                     help="multi-GPU: skip the extra measurement with every tree Morton-sharded")
+    ap.add_argument("--tensor-grid", default=None, choices=["always", "off"],
+                    help="first velocity evaluation of the tree-level step: sum factorisation at any size / never "
+                         "(default: on from 4 Mi points per call)")
     ap.add_argument("--exchange", default=None, choices=["peer", "nccl"],
                     help="multi-GPU: how outsiders travel (default: peer memory where available)")
     ap.add_argument("--replicate-velocity", action="store_true",

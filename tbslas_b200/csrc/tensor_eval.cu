@@ -387,6 +387,11 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// Fragment loads address (row = 4*step + l%4, col = base + l/4): with 16-double rows the four rows of
+// a fragment fall on the same banks (a 4-way conflict on every load).  XOR-ing the column with
+// 4*(row mod 4) spreads them over the banks without padding.
+__device__ __forceinline__ int swz(int row, int col) { return row * 16 + (col ^ ((row & 3) << 2)); }
+
 template <int D>
 __global__ void __launch_bounds__(kTensorThreads, 3)
 tensor_grid_dmma_kernel(const TensorParams p, const TensorTables tb_) {
@@ -436,13 +441,13 @@ tensor_grid_dmma_kernel(const TensorParams p, const TensorTables tb_) {
       const bool in = fabs(xi) <= 1.0;
       const double xc = in ? xi : 0.0, x2 = 2.0 * xc;
       double t0 = in ? 1.0 : 0.0, t1 = xc;
-      double *T = sT + a * 256 + i;  // [degree][point]
-      T[0] = t0;
-      if (D > 1) T[16] = t1;
+      double *T = sT + a * 256;  // [degree][point], swizzled
+      T[swz(0, i)] = t0;
+      if (D > 1) T[swz(1, i)] = t1;
 #pragma unroll
       for (int k = 2; k < D; k++) {
         const double t2 = __dsub_rn(__dmul_rn(x2, t1), t0);
-        T[k * 16] = t2;
+        T[swz(k, i)] = t2;
         t0 = t1;
         t1 = t2;
       }
@@ -461,7 +466,7 @@ tensor_grid_dmma_kernel(const TensorParams p, const TensorTables tb_) {
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int ks = 0; ks < KS; ks++) az[mt][ks] = sT[512 + (ks * 4 + lc) * 16 + mt * 8 + lr];
+        for (int ks = 0; ks < KS; ks++) az[mt][ks] = sT[512 + swz(ks * 4 + lc, mt * 8 + lr)];
       for (int l = 0; l < 3; l++) {
         const double *C = sC3 + l * p.ncoef_pad;
         // ---- pass 1: A1[r][px] = sum_k Cpad[r][k] Tx[k][px]
@@ -473,9 +478,9 @@ tensor_grid_dmma_kernel(const TensorParams p, const TensorTables tb_) {
           for (int ks = 0; ks < nks; ks++) {
             const int k = ks * 4 + lc;
             const double a = k < rlen ? C[roff + k] : 0.0;
-            dmma884(c0, c1, a, sT[k * 16 + nt * 8 + lr]);
+            dmma884(c0, c1, a, sT[swz(k, nt * 8 + lr)]);
           }
-          *reinterpret_cast<double2 *>(sA1 + r * 16 + nt * 8 + 2 * lc) = make_double2(c0, c1);
+          *reinterpret_cast<double2 *>(sA1 + swz(r, nt * 8 + 2 * lc)) = make_double2(c0, c1);
         }
         __syncthreads();
         // ---- pass 2: B2[i][py][px] = sum_j Ty[j][py] A1[(i,j)][px]
@@ -484,10 +489,10 @@ tensor_grid_dmma_kernel(const TensorParams p, const TensorTables tb_) {
           double c0 = 0.0, c1 = 0.0;
           for (int ks = 0; ks * 4 < nj; ks++) {
             const int jj = ks * 4 + lc;
-            const double b = jj < nj ? sA1[(rf + jj) * 16 + nt * 8 + lr] : 0.0;
-            dmma884(c0, c1, sT[256 + jj * 16 + mt * 8 + lr], b);
+            const double b = jj < nj ? sA1[swz(rf + jj, nt * 8 + lr)] : 0.0;
+            dmma884(c0, c1, sT[256 + swz(jj, mt * 8 + lr)], b);
           }
-          *reinterpret_cast<double2 *>(sB2 + i * 256 + (mt * 8 + lr) * 16 + nt * 8 + 2 * lc) = make_double2(c0, c1);
+          *reinterpret_cast<double2 *>(sB2 + i * 256 + (mt * 8 + lr) * 16 + ((nt * 8 + 2 * lc) ^ ((i & 3) << 2))) = make_double2(c0, c1);
         }
         __syncthreads();
         // ---- pass 3: U[pz][(py,px)] = sum_i Tz[i][pz] B2[i][(py,px)];  x' = x + alpha U on regular points
@@ -495,7 +500,7 @@ tensor_grid_dmma_kernel(const TensorParams p, const TensorTables tb_) {
           double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
           for (int ks = 0; ks < KS; ks++) {
-            const double b = sB2[(ks * 4 + lc) * 256 + nt * 8 + lr];
+            const double b = sB2[(ks * 4 + lc) * 256 + ((nt * 8 + lr) ^ (lc << 2))];
             dmma884(c[0][0], c[0][1], az[0][ks], b);
             dmma884(c[1][0], c[1][1], az[1][ks], b);
           }
