@@ -207,6 +207,13 @@ int tbslas_b200_semilag_rk2(const tbslas_field *f1, const tbslas_field *f2,
  * fewer than 4 Mi points keep the generic path (latency bound either way); mode 2 removes that
  * minimum (tests).  mode 0: every evaluation is point by point. */
 int tbslas_b200_set_tensor_grid(tbslas_ctx *ctx, int mode);
+/* Tree-level calls whose first velocity evaluation took the sum-factorised path need the arrival
+ * points once more, as the base of the RK2 update x' = x + tau*v(x_mid) (traj.inc:42).  on = 1:
+ * they are rebuilt there from (leaf geometry, node index) with the expressions that
+ * generate them -- the same bits -- instead of being written to and read back from HBM (48 B per
+ * point of traffic).  on = 0 (default): always materialised -- on C2 the saving in the first stage
+ * (7.6 -> 6.6 ms) is smaller than what the index decode costs the second evaluation (+5.2 ms). */
+int tbslas_b200_set_virtual_arrival_points(tbslas_ctx *ctx, int on);
 /* Calls with HOST buffers are cut into chunks whose copy-in, kernels and copy-out overlap on three
  * streams.  chunks = 0 (default): chosen from the bytes that cross PCIe (about 16 Mi points per chunk
  * for tree-level calls, 4 Mi with host input, at most 16); > 0: exactly that many.  In a multi-rank

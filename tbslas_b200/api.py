@@ -150,6 +150,11 @@ class Context:
         self.check(self.lib.tbslas_b200_comm_exchange_mode(self.h, C.byref(m), C.byref(c)))
         return ("peer" if m.value else "nccl"), int(c.value)
 
+    def set_virtual_arrival_points(self, on: bool) -> None:
+        """Tree-level calls: rebuild the arrival points where the step needs them again instead of
+        writing them to HBM (default on)."""
+        self.check(self.lib.tbslas_b200_set_virtual_arrival_points(self.h, int(bool(on))))
+
     def set_host_chunks(self, chunks: int) -> None:
         self.check(self.lib.tbslas_b200_set_host_chunks(self.h, int(chunks)))
 

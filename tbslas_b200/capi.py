@@ -24,7 +24,7 @@ SYMBOLS = [
     "tbslas_b200_synchronize", "tbslas_b200_set_time_combine", "tbslas_b200_cubic_time_weights", "tbslas_b200_set_tensor_grid", "tbslas_b200_last_grid_exceptions", "tbslas_b200_last_error", "tbslas_b200_version",
     "tbslas_b200_comm_unique_id", "tbslas_b200_comm_init", "tbslas_b200_comm_rank",
     "tbslas_b200_comm_last_exchange", "tbslas_b200_comm_set_exchange", "tbslas_b200_comm_set_mailbox",
-    "tbslas_b200_comm_exchange_mode", "tbslas_b200_tree_update_coeff_async", "tbslas_b200_set_host_chunks",
+    "tbslas_b200_comm_exchange_mode", "tbslas_b200_tree_update_coeff_async", "tbslas_b200_set_host_chunks", "tbslas_b200_set_virtual_arrival_points",
     "tbslas_b200_tree_create", "tbslas_b200_tree_create_replicated", "tbslas_b200_tree_update_coeff", "tbslas_b200_tree_get_coeff", "tbslas_b200_tree_destroy",
     "tbslas_b200_tree_info", "tbslas_b200_eval", "tbslas_b200_eval_set4",
     "tbslas_b200_eval_extrap", "tbslas_b200_eval_field", "tbslas_b200_traj_rk2",
@@ -83,6 +83,7 @@ def load() -> C.CDLL:
     L.tbslas_b200_comm_set_mailbox.argtypes = [vp, sz]
     L.tbslas_b200_comm_exchange_mode.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(sz)]
     L.tbslas_b200_set_host_chunks.argtypes = [vp, C.c_int]
+    L.tbslas_b200_set_virtual_arrival_points.argtypes = [vp, C.c_int]
     L.tbslas_b200_tree_update_coeff_async.argtypes = [vp, dp, C.c_int]
     L.tbslas_b200_tree_create.argtypes = [vp, C.c_int, C.c_int, sz, dp, vp, dp, C.c_int,
                                           C.POINTER(vp)]

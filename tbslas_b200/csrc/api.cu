@@ -118,13 +118,13 @@ int comm_tree_splitters(tbslas_tree *t, uint64_t first_key);
 int comm_begin_exchange(tbslas_ctx *ctx, const uint32_t *send_count_dev);
 int comm_forward_exchange(tbslas_tree *t, const double *send_pos, bool want_leaf);
 int comm_finish_exchange(tbslas_tree *t, int bc, const uint32_t *send_idx, int epilogue, double *out,
-                         const double *base, double alpha, int32_t *leaf_out);
+                         const double *base, double alpha, int32_t *leaf_out, const GridBase *gb);
 bool comm_peer_exchange(tbslas_ctx *ctx);
 int comm_check(tbslas_ctx *ctx);
 int px_begin(tbslas_tree *t, const uint32_t *send_count_dev, PxPack *pack);
 int px_packed(tbslas_ctx *ctx);
 int px_finish(tbslas_tree *t, int bc, const uint32_t *send_idx, size_t n_local, int epilogue, double *out,
-              const double *base, double alpha, int32_t *leaf_out);
+              const double *base, double alpha, int32_t *leaf_out, const GridBase *gb);
 void comm_destroy(tbslas_ctx *ctx);
 int comm_reshard(tbslas_tree *t, const size_t *new_first);
 
@@ -156,12 +156,14 @@ int tree_coeff_ready(const tbslas_tree *ct) {
 static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int epilogue,
                              double *out, const double *base, double alpha, int32_t *leaf_out,
                              bool allow_exchange, const tbslas_tree *same_as = nullptr,
-                             const uint32_t *n_dev = nullptr) {
+                             const uint32_t *n_dev = nullptr, const GridBase *gb = nullptr) {
   tbslas_ctx *ctx = t->ctx;
   if (n >= (size_t)0xfffffff0u)
     return fail(ctx, TBSLAS_ERR_INVALID, "n = %zu exceeds the 32-bit point index range", n);
-  if (epilogue == EPI_AXPY && t->dof != 3)
+  if (epilogue != EPI_STORE && t->dof != 3)
     return fail(ctx, TBSLAS_ERR_INVALID, "position update needs a dof-3 field (dof = %d)", t->dof);
+  if (epilogue == EPI_AXPY_GRID && (!gb || !eval_supports_grid_base(t)))
+    return fail(ctx, TBSLAS_ERR_INVALID, "grid-base epilogue not available for this tree");
   const int tile_pts = eval_tile_points(t);
   if (tile_pts <= 0)
     return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "Chebyshev degree %d not supported (1..%d)", t->q,
@@ -264,6 +266,7 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
   ea.out = out;
   ea.base = base;
   ea.alpha = alpha;
+  ea.grid = gb;
   TB_TRY(launch_cheb_eval(ctx, ea));
 
   if (leaf_out) {
@@ -272,10 +275,10 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
     TB_TRY(launch_leaf_fixup(ctx, leaf_out, n, t->n_leaf, t->leaf_offset));
   }
   if (peer) {
-    TB_TRY(px_finish(t, bc, (const uint32_t *)send_idx, n, epilogue, out, base, alpha, leaf_out));
+    TB_TRY(px_finish(t, bc, (const uint32_t *)send_idx, n, epilogue, out, base, alpha, leaf_out, gb));
   } else if (multi) {
     if (!exchange_first) TB_TRY(comm_forward_exchange(t, (const double *)send_pos, leaf_out != nullptr));
-    TB_TRY(comm_finish_exchange(t, bc, (const uint32_t *)send_idx, epilogue, out, base, alpha, leaf_out));
+    TB_TRY(comm_finish_exchange(t, bc, (const uint32_t *)send_idx, epilogue, out, base, alpha, leaf_out, gb));
   }
   return TBSLAS_OK;
 }
@@ -293,8 +296,8 @@ int eval_received_points(tbslas_tree *t, int bc, double *pos, size_t n, const ui
 
 static int eval_tree_dev(tbslas_tree *t, int bc, double *pos, size_t n, int epilogue, double *out,
                          const double *base, double alpha, int32_t *leaf_out,
-                         const tbslas_tree *same_as = nullptr) {
-  return eval_local_points(t, bc, pos, n, epilogue, out, base, alpha, leaf_out, true, same_as);
+                         const tbslas_tree *same_as = nullptr, const GridBase *gb = nullptr) {
+  return eval_local_points(t, bc, pos, n, epilogue, out, base, alpha, leaf_out, true, same_as, nullptr, gb);
 }
 
 static int check_field(tbslas_ctx **ctx_out, const tbslas_field *f, int *dof) {
@@ -355,17 +358,31 @@ static int field_single_tree(tbslas_ctx *ctx, const tbslas_field *f, double tq, 
   return TBSLAS_OK;
 }
 
+// whether field_single_tree will find one tree (no side effects: nothing is combined yet)
+static bool field_is_single(tbslas_ctx *ctx, const tbslas_field *f) {
+  if (f->kind == TBSLAS_FIELD_STEADY) return true;
+  if (!ctx->time_combine) return false;
+  const int nt = f->kind == TBSLAS_FIELD_SET4 ? 4 : 2;
+  for (int i = 1; i < nt; i++)
+    if (!same_leaves(f->tree[0], f->tree[i]) || f->tree[i]->replicated != f->tree[0]->replicated) return false;
+  return true;
+}
+
 // out = field(pos)                       (axpy == 0)
-// out = base + alpha * field(pos)        (axpy == 1; the RK2 position update)
+// out = base + alpha * field(pos)        (axpy == 1; the RK2 position update; `gb`: base is not an
+//                                         array but the grid points gb describes, rebuilt on the fly)
 static int eval_field_dev(const tbslas_field *f, double tq, int bc, double *pos, size_t n,
-                          double *out, int axpy, const double *base, double alpha) {
+                          double *out, int axpy, const double *base, double alpha,
+                          const GridBase *gb = nullptr) {
   tbslas_ctx *ctx;
   int dof;
   TB_TRY(check_field(&ctx, f, &dof));
   tbslas_tree view, *one = nullptr;
   TB_TRY(field_single_tree(ctx, f, tq, &view, &one));
+  if (gb && !one) return fail(ctx, TBSLAS_ERR_INVALID, "grid-base update needs a single-tree field");
   if (one) {
-    TB_TRY(eval_tree_dev(one, bc, pos, n, axpy ? EPI_AXPY : EPI_STORE, out, base, alpha, nullptr));
+    TB_TRY(eval_tree_dev(one, bc, pos, n, axpy ? (gb ? EPI_AXPY_GRID : EPI_AXPY) : EPI_STORE, out, base, alpha,
+                         nullptr, nullptr, gb));
     if (one == &view) f->tree[0]->pt_count_valid = view.pt_count_valid;
     return TBSLAS_OK;
   }
@@ -410,7 +427,7 @@ static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, 
   for (int s = 0; s < nrk; s++) {
     double *x = (s == 0 && x0) ? const_cast<double *>(x0) : xsol;  // not written unless periodic
     // v1 = V(x, t);  xtmp = x + 0.5*tau*v1      traj.inc:33-36 (x wrapped in place if periodic)
-    bool done = false;
+    bool done = false, virtual_x = false;
     if (s == 0 && grid && x == xsol) {
       const size_t P = (size_t)(grid->q + 1) * (grid->q + 1) * (grid->q + 1);
       // small point sets are latency bound either way; a Morton-sharded velocity tree makes the
@@ -422,11 +439,18 @@ static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, 
         tbslas_tree view, *one = nullptr;
         TB_TRY(field_single_tree(ctx, f1, tcur, &view, &one));
         if (one) {
-          const int rc = launch_tensor_grid_eval(ctx, one, grid, leaf0, n / P, bc, x, xtmp, 0.5 * tau, gen_points);
-          if (rc == TBSLAS_OK)
+          // Virtual x: when the points are generated here and the second stage can rebuild them
+          // in its epilogue (one tree, persistent kernel), the arrival points are never written.
+          const tbslas_field *fs2 = f2 ? f2 : f1;
+          const bool virt = gen_points && ctx->virtual_x && tensor_grid_supports_virtual_x(one) &&
+                            field_is_single(ctx, fs2) && eval_supports_grid_base(fs2->tree[0]);
+          const int rc = launch_tensor_grid_eval(ctx, one, grid, leaf0, n / P, bc, x, xtmp, 0.5 * tau, gen_points, virt);
+          if (rc == TBSLAS_OK) {
             done = true;
-          else if (rc != TBSLAS_ERR_UNSUPPORTED)
+            virtual_x = virt;
+          } else if (rc != TBSLAS_ERR_UNSUPPORTED) {
             return rc;
+          }
         }
       }
       // `gen_points`: the start points are still to be written (CollectChebTreeGridPoints)
@@ -434,7 +458,13 @@ static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, 
     }
     if (!done) TB_TRY(eval_field_dev(f1, tcur, bc, x, n, xtmp, 1, x, 0.5 * tau));
     // v2 = V(xtmp, t + tau/2);  x = x + tau*v2  traj.inc:40-42
-    TB_TRY(eval_field_dev(f2 ? f2 : f1, tcur + 0.5 * tau, bc, xtmp, n, xsol, 1, x, tau));
+    if (virtual_x) {
+      GridBase gb;
+      make_grid_base(grid, leaf0, bc, &gb);
+      TB_TRY(eval_field_dev(f2 ? f2 : f1, tcur + 0.5 * tau, bc, xtmp, n, xsol, 1, nullptr, tau, &gb));
+    } else {
+      TB_TRY(eval_field_dev(f2 ? f2 : f1, tcur + 0.5 * tau, bc, xtmp, n, xsol, 1, x, tau));
+    }
     tcur = tcur + tau;
   }
   return TBSLAS_OK;
@@ -824,6 +854,12 @@ int tbslas_b200_set_time_combine(tbslas_ctx *ctx, int mode) {
 int tbslas_b200_last_grid_exceptions(tbslas_ctx *ctx, size_t *n) {
   if (!ctx || !n) return TBSLAS_ERR_INVALID;
   *n = ctx->last_exceptions;
+  return TBSLAS_OK;
+}
+
+int tbslas_b200_set_virtual_arrival_points(tbslas_ctx *ctx, int on) {
+  if (!ctx || (on != 0 && on != 1)) return TBSLAS_ERR_INVALID;
+  ctx->virtual_x = on;
   return TBSLAS_OK;
 }
 

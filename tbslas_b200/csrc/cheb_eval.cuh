@@ -25,6 +25,7 @@
 // path only by rounding of the accumulation (<< 1e-12 relative to the field scale).
 #pragma once
 #include "common.cuh"
+#include "gridbase.cuh"
 
 namespace tb {
 
@@ -45,6 +46,7 @@ struct EvalParams {
   double *out;
   const double *base;
   double alpha;
+  GridBase gb;           // EPI_AXPY_GRID only
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

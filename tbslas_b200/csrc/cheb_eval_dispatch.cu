@@ -35,7 +35,8 @@ static int eval_kind(int q, size_t stride) {
   if (q > kMaxUnrolledDeg) return 2;
   if (eval_variant() == 1 && (q == 8 || q == 14)) return 1;
   if (eval_variant() == 2) return 2;
-  const size_t smem = (stride + 11 * 32 * (size_t)eval_ppt(q) + 16) * sizeof(double);
+  // (13 * 32 * PPT: the largest staging area, that of the grid-base epilogue)
+  const size_t smem = (stride + 13 * 32 * (size_t)eval_ppt(q) + 16) * sizeof(double);
   return smem <= kWtSmemLimit ? 0 : 2;
 }
 
@@ -49,10 +50,13 @@ int eval_tile_points(const tbslas_tree *t) {
 }
 
 bool eval_needs_tile_map(const tbslas_tree *t) { return eval_kind(t->q, t->stride) != 0; }
+bool eval_supports_grid_base(const tbslas_tree *t) { return eval_kind(t->q, t->stride) == 0 && t->dof == 3; }
 
 int launch_cheb_eval(tbslas_ctx *ctx, const EvalArgs &a) {
   StageScope sc(ctx, ST_CHEB_EVAL, (double)a.n, 1);
   const int kind = eval_kind(a.tree->q, a.tree->stride);
+  if (a.epilogue == EPI_AXPY_GRID && kind != 0)
+    return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "grid-base epilogue needs the persistent evaluation kernel");
   if (kind == 2) return launch_cheb_eval_generic(ctx, a);
   if (kind == 1)
     return a.tree->q == 8 ? launch_cheb_eval_q<8, eval_ppt(8)>(ctx, a) : launch_cheb_eval_q<14, eval_ppt(14)>(ctx, a);

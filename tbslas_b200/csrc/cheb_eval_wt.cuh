@@ -25,6 +25,9 @@ namespace tb {
 __device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_4(void *dst_smem, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
@@ -38,7 +41,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int PPT, int EPI>
 struct WarpStage {
   static constexpr int TP = 32 * PPT;
-  static constexpr int kBase = (EPI == EPI_AXPY) ? 6 * TP : 0;
+  // RK2 base: 2 x [3][TP] coordinates (EPI_AXPY), or 2 x [TP] leaf geometries of 4 doubles (EPI_AXPY_GRID)
+  static constexpr int kBase = (EPI == EPI_AXPY) ? 6 * TP : (EPI == EPI_AXPY_GRID ? 8 * TP : 0);
   static constexpr int kPermDoubles = (3 * TP + 1) / 2;
   static constexpr int kDoubles = 3 * TP + 4 + kBase + kPermDoubles + (kPermDoubles & 1) + 8;
 };
@@ -199,6 +203,12 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
         cp_async_8(d + TP, bp + 1);
         cp_async_8(d + 2 * TP, bp + 2);
       }
+      if (EPI == EPI_AXPY_GRID) {  // geometry of the grid leaf the point is a node of
+        const double4 *gp = p.gb.ggeom + (unsigned)i / p.gb.P;
+        double *d = s_b + ((n & 1) * TP + o) * 4;
+        cp_async_16(d, gp);
+        cp_async_16(d + 2, reinterpret_cast<const double *>(gp) + 2);
+      }
     }
     if (lane < 4) cp_async_8(s_g + lane, reinterpret_cast<const double *>(p.geom + leaf) + lane);
   };
@@ -280,8 +290,11 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
           const size_t i = s_perm[(n % 3) * TP + o];
           if (EPI == EPI_STORE) {
             p.out[i * p.dof + l] = u[s];
-          } else {  // x' = x0 + alpha * v, multiply then add as traj.inc:36,42
+          } else if (EPI == EPI_AXPY) {  // x' = x0 + alpha * v, multiply then add as traj.inc:36,42
             p.out[3 * i + l] = __dadd_rn(s_b[(n & 1) * 3 * TP + l * TP + o], __dmul_rn(p.alpha, u[s]));
+          } else {  // the same with x0 rebuilt from its leaf's geometry and its node index
+            const double4 g = *reinterpret_cast<const double4 *>(s_b + ((n & 1) * TP + o) * 4);
+            p.out[3 * i + l] = __dadd_rn(grid_base_coord(p.gb, g, (unsigned)i, l), __dmul_rn(p.alpha, u[s]));
           }
         }
       }
@@ -319,6 +332,10 @@ int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
   p.out = a.out;
   p.base = a.base;
   p.alpha = a.alpha;
+  if (a.epilogue == EPI_AXPY_GRID) {
+    if (!a.grid) return fail(ctx, TBSLAS_ERR_INVALID, "grid epilogue without a grid");
+    p.gb = *a.grid;
+  }
   // every CTA (one warp) is a worker: no more workers than tiles, at most 8 per SM
   size_t grid = a.max_tiles;
   if (grid > (size_t)8 * ctx->n_sm) grid = (size_t)8 * ctx->n_sm;
@@ -332,9 +349,15 @@ int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
     if (smem > 48 * 1024)
       TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk);
-  } else {
+  } else if (a.epilogue == EPI_AXPY) {
     const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_AXPY>(t);
     auto k = cheb_eval_wt_kernel<Q, PPT, EPI_AXPY>;
+    if (smem > 48 * 1024)
+      TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk);
+  } else {
+    const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_AXPY_GRID>(t);
+    auto k = cheb_eval_wt_kernel<Q, PPT, EPI_AXPY_GRID>;
     if (smem > 48 * 1024)
       TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk);

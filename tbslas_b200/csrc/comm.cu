@@ -27,6 +27,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "gridbase.cuh"
 
 namespace tb {
 
@@ -269,7 +270,7 @@ template <int EPI>
 __global__ void unpack_kernel(const double *__restrict__ val, const int32_t *__restrict__ leaf_in,
                               const uint32_t *__restrict__ idx, size_t m, const uint32_t *__restrict__ m_dev,
                               int dof, double *__restrict__ out, const double *__restrict__ base, double alpha,
-                              int32_t *__restrict__ leaf_out) {
+                              int32_t *__restrict__ leaf_out, const GridBase gb) {
   if (m_dev) m = *m_dev;
   const size_t total = m * dof, step = (size_t)gridDim.x * blockDim.x;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {  // one scalar each
@@ -279,8 +280,11 @@ __global__ void unpack_kernel(const double *__restrict__ val, const int32_t *__r
     const double u = val[e];
     if (EPI == EPI_STORE) {
       out[i * dof + l] = u;
-    } else {  // same expression as the eval kernel's epilogue (traj.inc:36,42)
+    } else if (EPI == EPI_AXPY) {  // same expression as the eval kernel's epilogue (traj.inc:36,42)
       out[3 * i + l] = __dadd_rn(base[3 * i + l], __dmul_rn(alpha, u));
+    } else {  // base rebuilt from the grid (gridbase.cuh)
+      const double4 g = gb.ggeom[(unsigned)i / gb.P];
+      out[3 * i + l] = __dadd_rn(grid_base_coord(gb, g, (unsigned)i, l), __dmul_rn(alpha, u));
     }
     if (leaf_out && l == 0) leaf_out[i] = leaf_in[s];
   }
@@ -651,7 +655,7 @@ int px_packed(tbslas_ctx *ctx) {
 
 // after the insiders: evaluate what arrived, return the values, unpack mine
 int px_finish(tbslas_tree *t, int bc, const uint32_t *send_idx, size_t n_local, int epilogue, double *out,
-              const double *base, double alpha, int32_t *leaf_out) {
+              const double *base, double alpha, int32_t *leaf_out, const GridBase *gb) {
   tbslas_ctx *ctx = t->ctx;
   ExchangeState &x = xs_of(ctx);
   const int np = ctx->nranks, me = ctx->rank, dof = t->dof;
@@ -681,12 +685,16 @@ int px_finish(tbslas_tree *t, int bc, const uint32_t *send_idx, size_t n_local, 
     StageScope sc(ctx, ST_UNPACK, 0.0, 1);
     const double *rv = reinterpret_cast<const double *>(x.mailbox + x.lay.off_ret_val());
     const int32_t *rl = reinterpret_cast<const int32_t *>(x.mailbox + x.lay.off_ret_leaf());
+    const GridBase gbv = gb ? *gb : GridBase();
     if (epilogue == EPI_STORE)
       unpack_kernel<EPI_STORE><<<g, 256, 0, ctx->stream>>>(rv, rl, send_idx, 0, &x.d_info->n_send, dof, out, base,
-                                                          alpha, leaf_out);
-    else
+                                                          alpha, leaf_out, gbv);
+    else if (epilogue == EPI_AXPY)
       unpack_kernel<EPI_AXPY><<<g, 256, 0, ctx->stream>>>(rv, rl, send_idx, 0, &x.d_info->n_send, dof, out, base,
-                                                         alpha, leaf_out);
+                                                         alpha, leaf_out, gbv);
+    else
+      unpack_kernel<EPI_AXPY_GRID><<<g, 256, 0, ctx->stream>>>(rv, rl, send_idx, 0, &x.d_info->n_send, dof, out,
+                                                              base, alpha, leaf_out, gbv);
     TB_CUDA(ctx, cudaGetLastError());
   }
   return TBSLAS_OK;
@@ -747,7 +755,7 @@ int comm_forward_exchange(tbslas_tree *t, const double *send_pos, bool want_leaf
 
 // Step 3: evaluation of what arrived, reverse exchange, unpack.
 int comm_finish_exchange(tbslas_tree *t, int bc, const uint32_t *send_idx, int epilogue, double *out,
-                         const double *base, double alpha, int32_t *leaf_out) {
+                         const double *base, double alpha, int32_t *leaf_out, const GridBase *gb) {
   tbslas_ctx *ctx = t->ctx;
   ExchangeState &x = xs_of(ctx);
   const int dof = t->dof;
@@ -764,12 +772,17 @@ int comm_finish_exchange(tbslas_tree *t, int bc, const uint32_t *send_idx, int e
     StageScope sc(ctx, ST_UNPACK, (double)x.n_send, 1);
     const size_t m = x.n_send * dof;
     const unsigned grid = (unsigned)((m + 255) / 256);
+    const GridBase gbv = gb ? *gb : GridBase();
     if (epilogue == EPI_STORE)
       unpack_kernel<EPI_STORE><<<grid, 256, 0, ctx->stream>>>((const double *)x.ret_val, (const int32_t *)x.ret_leaf,
-                                                            send_idx, x.n_send, nullptr, dof, out, base, alpha, leaf_out);
-    else
+                                                            send_idx, x.n_send, nullptr, dof, out, base, alpha, leaf_out, gbv);
+    else if (epilogue == EPI_AXPY)
       unpack_kernel<EPI_AXPY><<<grid, 256, 0, ctx->stream>>>((const double *)x.ret_val, (const int32_t *)x.ret_leaf,
-                                                           send_idx, x.n_send, nullptr, dof, out, base, alpha, leaf_out);
+                                                           send_idx, x.n_send, nullptr, dof, out, base, alpha, leaf_out, gbv);
+    else
+      unpack_kernel<EPI_AXPY_GRID><<<grid, 256, 0, ctx->stream>>>((const double *)x.ret_val, (const int32_t *)x.ret_leaf,
+                                                                send_idx, x.n_send, nullptr, dof, out, base, alpha,
+                                                                leaf_out, gbv);
     TB_CUDA(ctx, cudaGetLastError());
   }
   return TBSLAS_OK;

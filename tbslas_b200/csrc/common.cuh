@@ -137,6 +137,11 @@ struct tbslas_ctx {
   int tensor_grid = 1;
   size_t tensor_grid_min_points = (size_t)4 << 20;  // tbslas_b200_set_tensor_grid(ctx, 2): no minimum
   size_t last_exceptions = 0;  // arrival points of the last such call that took the generic path
+  // tree-level calls: 1 = the arrival points are never written to HBM when the step can rebuild them
+  // from (leaf geometry, node index) where it needs them again (gridbase.cuh); 0 (default) = always
+  // materialised.  Measured on C2: the tensor stage drops from 7.6 to 6.6 ms, but the index decode in
+  // the second evaluation's epilogue costs 5.2 ms -- a net loss, so it is an option, not the default.
+  int virtual_x = 0;
   // How many arrival points of a (grid leaf range, velocity tree) pair take the generic path is a
   // property of the two leaf lists and the boundary condition alone, so it is read back from the
   // device ONCE per pair and remembered: steps on unchanged trees never wait for the device.
@@ -261,7 +266,15 @@ struct BinArgs {
 int launch_bin(tbslas_ctx *ctx, const BinArgs &a);
 
 // cheb_eval_*.cu
-enum Epilogue { EPI_STORE = 0, EPI_AXPY = 1 };
+// EPI_AXPY_GRID: as EPI_AXPY, with base[i] rebuilt from (leaf geometry, node index) instead of read
+// (gridbase.cuh): tree-level steps never materialise their arrival points
+enum Epilogue { EPI_STORE = 0, EPI_AXPY = 1, EPI_AXPY_GRID = 2 };
+struct GridBase {
+  const double4 *ggeom = nullptr;  // geometry of the grid tree's leaves, offset to the call's first leaf
+  unsigned P = 1, D = 1;           // points per leaf (D^3), nodes per axis
+  int periodic = 0;
+  double node[TBSLAS_MAX_CHEB_DEG + 1];  // tbslas::new_nodes, 1-D
+};
 struct EvalArgs {
   const tbslas_tree *tree;
   const double *pos;       // [n][3]
@@ -276,9 +289,11 @@ struct EvalArgs {
   double *out;             // STORE: [n][dof]; AXPY: [n][3] = base + alpha*value (dof must be 3)
   const double *base;
   double alpha;
+  const GridBase *grid = nullptr;  // EPI_AXPY_GRID
 };
 int eval_tile_points(const tbslas_tree *t);   // points per tile of the kernel that will run
 bool eval_needs_tile_map(const tbslas_tree *t);  // only the one-tile-per-CTA kernels index a tile map
+bool eval_supports_grid_base(const tbslas_tree *t);  // EPI_AXPY_GRID: the persistent kernel only
 int launch_cheb_eval(tbslas_ctx *ctx, const EvalArgs &a);
 
 // combine.cu
@@ -305,7 +320,10 @@ int set_pt2coeff(tbslas_ctx *ctx, int q, const double *M_host);
 int launch_refit(tbslas_ctx *ctx, tbslas_tree *t, const double *vals, int point_major);
 // tensor_eval.cu
 int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree *grid, size_t leaf0,
-                            size_t n_leaf, int bc, double *x, double *out, double alpha, bool gen_points);
+                            size_t n_leaf, int bc, double *x, double *out, double alpha, bool gen_points,
+                            bool virtual_x);
+bool tensor_grid_supports_virtual_x(const tbslas_tree *vel);
+void make_grid_base(const tbslas_tree *grid, size_t leaf0, int bc, GridBase *gb);
 // tailnorm.cu
 int launch_tail_norm(tbslas_ctx *ctx, const tbslas_tree *t, double *out);
 // peak.cu

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gridbase.cuh"
 #include "keys.cuh"
 
 namespace tb {
@@ -561,6 +562,17 @@ __global__ void gather_points_kernel(const double *__restrict__ x, const uint32_
   const size_t s = e / 3;
   out[e] = x[3 * (size_t)idx[s] + (e - 3 * s)];
 }
+// the same for arrival points that were never written (virtual x): rebuilt from the grid
+__global__ void gather_grid_points_kernel(const GridBase gb, const uint32_t *__restrict__ idx, size_t m,
+                                          double *__restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * m) return;
+  const size_t s = e / 3;
+  const unsigned i = idx[s];
+  GridBase raw = gb;
+  raw.periodic = 0;  // the evaluation that follows wraps, exactly as it would wrap a stored point
+  out[e] = grid_base_coord(raw, gb.ggeom[i / gb.P], i, (int)(e - 3 * s));
+}
 __global__ void scatter_update_kernel(const double *__restrict__ pos, const double *__restrict__ val,
                                       const uint32_t *__restrict__ idx, size_t m, double alpha, int periodic,
                                       double *__restrict__ x, double *__restrict__ out) {
@@ -568,7 +580,7 @@ __global__ void scatter_update_kernel(const double *__restrict__ pos, const doub
   if (e >= 3 * m) return;
   const size_t s = e / 3, o = 3 * (size_t)idx[s] + (e - 3 * s);
   const double b = pos[e];  // wrapped in place by the evaluation when periodic (tree_functor.h:442-449)
-  if (periodic) x[o] = b;
+  if (periodic && x) x[o] = b;
   out[o] = __dadd_rn(b, __dmul_rn(alpha, val[e]));
 }
 
@@ -580,8 +592,21 @@ __global__ void scatter_update_kernel(const double *__restrict__ pos, const doub
 // exceptions of a Morton-sharded velocity tree is a collective evaluation.
 int eval_tree_dev_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out);  // api.cu
 
+void make_grid_base(const tbslas_tree *grid, size_t leaf0, int bc, GridBase *gb) {
+  const int d = grid->q + 1;
+  gb->ggeom = grid->d_geom + leaf0;
+  gb->D = (unsigned)d;
+  gb->P = (unsigned)(d * d * d);
+  gb->periodic = bc == TBSLAS_PERIODIC;
+  new_nodes_host(grid->q, gb->node);
+}
+
+// virtual x: only the kernels that rebuild the grid points themselves (compile-time degrees)
+bool tensor_grid_supports_virtual_x(const tbslas_tree *vel) { return vel->q + 1 <= 15; }
+
 int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree *grid, size_t leaf0,
-                            size_t n_leaf, int bc, double *x, double *out, double alpha, bool gen_points) {
+                            size_t n_leaf, int bc, double *x, double *out, double alpha, bool gen_points,
+                            bool virtual_x) {
   const bool collective = ctx->nranks > 1 && !vel->replicated;
   if (vel->dof != 3 || vel->q != grid->q || !vel->boxes_all || !grid->boxes_all || (!collective && !vel->n_leaf))
     return TBSLAS_ERR_UNSUPPORTED;
@@ -632,7 +657,7 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
     p.d = d;
     p.periodic = periodic;
     p.x = x;
-    p.xgen = gen_points ? x : nullptr;
+    p.xgen = (gen_points && !virtual_x) ? x : nullptr;  // virtual x: the arrival points are never written
     p.out = out;
     p.alpha = alpha;
     p.exc_count = exc_count;
@@ -707,7 +732,13 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
   const unsigned g3 = (unsigned)((3 * m + 255) / 256);
   if (m) {
     StageScope sc(ctx, ST_TENSOR, 0.0, 1);
-    gather_points_kernel<<<g3, 256, 0, ctx->stream>>>(x, (const uint32_t *)exc_idx, m, (double *)epos);
+    if (virtual_x) {
+      GridBase gb;
+      make_grid_base(grid, leaf0, bc, &gb);
+      gather_grid_points_kernel<<<g3, 256, 0, ctx->stream>>>(gb, (const uint32_t *)exc_idx, m, (double *)epos);
+    } else {
+      gather_points_kernel<<<g3, 256, 0, ctx->stream>>>(x, (const uint32_t *)exc_idx, m, (double *)epos);
+    }
     TB_CUDA(ctx, cudaGetLastError());
   }
   TB_TRY(eval_tree_dev_points(vel, bc, (double *)epos, m, (double *)eval));
@@ -715,7 +746,7 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
     StageScope sc(ctx, ST_TENSOR, 0.0, 1);
     scatter_update_kernel<<<g3, 256, 0, ctx->stream>>>((const double *)epos, (const double *)eval,
                                                        (const uint32_t *)exc_idx, m, alpha,
-                                                       periodic, x, out);
+                                                       periodic, virtual_x ? nullptr : x, out);
     TB_CUDA(ctx, cudaGetLastError());
   }
   return TBSLAS_OK;

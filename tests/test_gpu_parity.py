@@ -558,6 +558,35 @@ def test_gpu_cubic_grid_vs_oracle(ctx, port):
                               port.fast_interp(grid, dof, n_reg, pts))
 
 
+@pytest.mark.parametrize("bc", [0, 1])
+def test_gpu_virtual_arrival_points_same_bits(ctx, bc):
+    """tbslas_b200_set_virtual_arrival_points: rebuilding the arrival points in the second stage's
+    epilogue (never writing them to HBM) gives the very bits of the materialised path -- steady and
+    4-snapshot velocity, nrk 1 and 2, values and departure points."""
+    api = _api()
+    q = 8
+    coord, dd = adaptive_leaves(4, 2)
+    vc, vd = ftm.uniform_leaves(2)
+    tcon = ctx.tree(ftm.random_tree(coord, dd, q, 1, seed=3))
+    fv = [ftm.random_tree(vc, vd, q, 3, seed=50 + k, scale=0.3) for k in range(4)]
+    tv = [ctx.tree(f) for f in fv]
+    ctx.set_tensor_grid("always")
+    try:
+        for vel in (api.NodeFieldFunctor(tv[0]), api.FieldSetFunctor(tv, [-0.05, 0.0, 0.05, 0.1])):
+            for nrk in (1, 2):
+                ctx.set_virtual_arrival_points(False)
+                a, da = api.SolveSemilagInSitu(vel, tcon, 1, 0.04, nrk, bc, departure_points=True)
+                ctx.set_virtual_arrival_points(True)
+                b, db = api.SolveSemilagInSitu(vel, tcon, 1, 0.04, nrk, bc, departure_points=True)
+                assert ctx.last_grid_exceptions() > 0
+                assert np.array_equal(a, b) and np.array_equal(da, db)
+    finally:
+        ctx.set_virtual_arrival_points(False)
+        ctx.set_tensor_grid(True)
+        for t in tv + [tcon]:
+            t.destroy()
+
+
 def test_gpu_resident_cubic_grid_handle(ctx, port):
     """tbslas_b200_grid_create/eval/update/destroy: the same bits as the one-shot call, host and
     device buffers, chunked host pipeline included."""
