@@ -43,9 +43,11 @@ sys.path.insert(0, ROOT)
 
 def measured_traffic(workload, scale):
     """DRAM bytes per launch of the evaluation kernel from the committed ncu capture of this
-    very command (profiles/r01_dram_cheb_eval_c2.csv: dram__bytes_read.sum + dram__bytes_write.sum
+    very command (profiles/r02_dram_cheb_eval_c2.csv: dram__bytes_read.sum + dram__bytes_write.sum
     of the three launches of one full-size C2 step), or None for other workloads."""
-    p = os.path.join(ROOT, "profiles", "r01_dram_cheb_eval_c2.csv")
+    p = os.path.join(ROOT, "profiles", "r02_dram_cheb_eval_c2.csv")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_dram_cheb_eval_c2.csv")
     if workload.lower() != "c2" or scale != 0 or not os.path.exists(p):
         return None, None
     import csv
@@ -55,7 +57,7 @@ def measured_traffic(workload, scale):
             per[row[0]] = per.get(row[0], 0.0) + float(row[14])
     if not per:
         return None, None
-    return sum(per.values()) / len(per), "profiles/r01_dram_cheb_eval_c2.csv (ncu, %d launches of one step)" % len(per)
+    return sum(per.values()) / len(per), "profiles/%s (ncu, %d launches of one step)" % (os.path.basename(p), len(per))
 
 
 def load_peaks():

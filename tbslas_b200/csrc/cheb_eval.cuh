@@ -46,7 +46,6 @@ struct EvalParams {
   double *out;
   const double *base;
   double alpha;
-  GridBase gb;           // EPI_AXPY_GRID only
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

@@ -71,7 +71,7 @@ constexpr int kWtThreads = 32;  // one warp per CTA: every address below is CTA-
 // takes more chunks and all workers finish together.
 template <int Q, int PPT, int EPI>
 __global__ void __launch_bounds__(kWtThreads, TB_WT_MINB)
-cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, unsigned chunk) {
+cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, unsigned chunk, const GridBase gb) {
   constexpr int D = Q + 1;
   constexpr int TP = 32 * PPT;
   typedef WarpStage<PPT, EPI> Stage;
@@ -204,7 +204,7 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
         cp_async_8(d + 2 * TP, bp + 2);
       }
       if (EPI == EPI_AXPY_GRID) {  // geometry of the grid leaf the point is a node of
-        const double4 *gp = p.gb.ggeom + (unsigned)i / p.gb.P;
+        const double4 *gp = gb.ggeom + (unsigned)i / gb.P;
         double *d = s_b + ((n & 1) * TP + o) * 4;
         cp_async_16(d, gp);
         cp_async_16(d + 2, reinterpret_cast<const double *>(gp) + 2);
@@ -294,7 +294,7 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
             p.out[3 * i + l] = __dadd_rn(s_b[(n & 1) * 3 * TP + l * TP + o], __dmul_rn(p.alpha, u[s]));
           } else {  // the same with x0 rebuilt from its leaf's geometry and its node index
             const double4 g = *reinterpret_cast<const double4 *>(s_b + ((n & 1) * TP + o) * 4);
-            p.out[3 * i + l] = __dadd_rn(grid_base_coord(p.gb, g, (unsigned)i, l), __dmul_rn(p.alpha, u[s]));
+            p.out[3 * i + l] = __dadd_rn(grid_base_coord(gb, g, (unsigned)i, l), __dmul_rn(p.alpha, u[s]));
           }
         }
       }
@@ -332,9 +332,10 @@ int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
   p.out = a.out;
   p.base = a.base;
   p.alpha = a.alpha;
+  GridBase gb;
   if (a.epilogue == EPI_AXPY_GRID) {
     if (!a.grid) return fail(ctx, TBSLAS_ERR_INVALID, "grid epilogue without a grid");
-    p.gb = *a.grid;
+    gb = *a.grid;
   }
   // every CTA (one warp) is a worker: no more workers than tiles, at most 8 per SM
   size_t grid = a.max_tiles;
@@ -348,19 +349,19 @@ int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
     auto k = cheb_eval_wt_kernel<Q, PPT, EPI_STORE>;
     if (smem > 48 * 1024)
       TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk);
+    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk, gb);
   } else if (a.epilogue == EPI_AXPY) {
     const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_AXPY>(t);
     auto k = cheb_eval_wt_kernel<Q, PPT, EPI_AXPY>;
     if (smem > 48 * 1024)
       TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk);
+    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk, gb);
   } else {
     const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_AXPY_GRID>(t);
     auto k = cheb_eval_wt_kernel<Q, PPT, EPI_AXPY_GRID>;
     if (smem > 48 * 1024)
       TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk);
+    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk, gb);
   }
   TB_CUDA(ctx, cudaGetLastError());
   return TBSLAS_OK;
