@@ -178,6 +178,12 @@ int comm_tree_splitters(tbslas_tree *t, uint64_t first_key) {
   return TBSLAS_OK;
 }
 
+// all-gather of `bytes` bytes per rank on the context's stream (no host synchronisation)
+int comm_allgather_bytes(tbslas_ctx *ctx, const void *mine, void *all, size_t bytes) {
+  TB_NCCL(ctx, g_nccl.AllGather(mine, all, bytes, ncclUint8, comm_of(ctx), ctx->stream));
+  return TBSLAS_OK;
+}
+
 // ---------------------------------------------------------------------------
 // co-partitioning: leaves move between ranks (tbslas::SemiMergeTree -> pvfmm RedistNodes,
 // tree_utils.h:609-729: the reference recomputes break points and MOVES the nodes)
@@ -641,6 +647,7 @@ int px_begin(tbslas_tree *t, const uint32_t *send_count_dev, PxPack *pack) {
   pack->dst_off = x.d_info->dst_off;
   pack->peer_base = x.d_peers->base;
   pack->off_recv_pos = x.lay.off_recv_pos();
+  pack->skip = &x.d_info->overflow;  // followed by `timeout`
   return TBSLAS_OK;
 }
 

@@ -71,6 +71,7 @@ enum Slot {
   WS_EXC_IDX,    // uint32 [n] arrival points that need the generic evaluation
   WS_EXC_POS,
   WS_EXC_VAL,
+  WS_GHOST,      // last leaf of every rank (tensor-grid path over a Morton-sharded velocity tree)
   WS_COUNT_SLOTS
 };
 
@@ -98,6 +99,7 @@ struct PxPack {  // where the pack kernel puts outsiders in peer-exchange mode (
   const uint32_t *dst_off = nullptr;   // [nranks] where my bucket starts in the owner's receive buffer
   char *const *peer_base = nullptr;    // [nranks] mapped mailboxes (device table)
   size_t off_recv_pos = 0;
+  const uint32_t *skip = nullptr;      // [2] {overflow, timeout}: non-zero = nothing may be written to a peer
 };
 
 }  // namespace tb

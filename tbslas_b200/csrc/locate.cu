@@ -389,6 +389,7 @@ __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint
                                     const uint32_t *__restrict__ send_count, int nranks,
                                     double *__restrict__ send_pos, uint32_t *__restrict__ send_idx, PxPack px) {
   __shared__ unsigned s_off[kMaxRanks], s_dst[kMaxRanks];
+  __shared__ unsigned s_skip;
   if (MODE == 1) {
     if (threadIdx.x == 0) {
       unsigned run = 0;
@@ -404,6 +405,9 @@ __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint
       s_off[threadIdx.x] = px.send_off[threadIdx.x];
       s_dst[threadIdx.x] = px.dst_off[threadIdx.x];
     }
+    // a count matrix that does not fit the mailboxes (or a peer that never arrived): the offsets would
+    // point past the owners' buffers, so nothing travels; the error is raised at the next host sync
+    if (threadIdx.x == 0) s_skip = px.skip[0] | px.skip[1];
     __syncthreads();
   }
   if (n_dev) {
@@ -421,7 +425,7 @@ __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint
     send_pos[3 * (size_t)slot + 1] = pos[3 * i + 1];
     send_pos[3 * (size_t)slot + 2] = pos[3 * i + 2];
     send_idx[slot] = (uint32_t)i;
-  } else if (MODE == 2) {
+  } else if (MODE == 2 && !s_skip) {
     const int o = -2 - j;
     const unsigned r = rank[i];
     double *dst = reinterpret_cast<double *>(px.peer_base[o] + px.off_recv_pos) + 3 * ((size_t)s_dst[o] + r);

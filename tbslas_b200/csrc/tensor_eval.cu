@@ -45,11 +45,67 @@ struct TensorTables {
   uint8_t tile_k[(kMaxRows + 7) / 8];  // longest row of every 8-row tile (DMMA kernel: k-steps of pass 1)
 };
 
-// grid leaf -> velocity leaf that contains its box, or -1
+// Ghost leaves (Morton-sharded velocity tree): the LAST leaf of every rank, all-gathered per call.  An
+// advected leaf whose containing velocity leaf lives on another rank always lies under that rank's last
+// leaf (leaves are disjoint and Morton ordered, and both trees share the split keys), so with these few
+// records the sum-factorised path covers exactly the leaves it covers when the velocity tree is held
+// whole -- instead of sending all their points through the generic, exchanged evaluation.  Record of
+// rank r at ghost + r*ghost_rec: {uint4 box; double4 geom; u64 n_leaf; u64 pad; double coeff[vstride]}.
+constexpr size_t kGhostHdr = 64;
+struct TensorParams {
+  const double *vcoeff;     // velocity coefficients, [leaf][dof][ncoef_pad]
+  const double4 *vgeom;
+  const uint4 *vbox;
+  int v_nleaf;              // local velocity leaves; map values >= v_nleaf name the ghost of rank (j - v_nleaf)
+  const char *ghost;        // nullptr: no ghosts
+  size_t ghost_rec;
+  unsigned vstride, ncoef_pad;
+  const double4 *ggeom;     // grid tree, already offset to the first leaf of the range
+  const uint8_t *gdepth;
+  const int32_t *map;
+  size_t n_leaf;
+  int d, periodic;
+  const double *x;          // [n_leaf * P][3] the grid points
+  double *xgen;             // != nullptr: the grid points are WRITTEN here first (== x): the kernel is
+                            // also tbslas::CollectChebTreeGridPoints (gridpts.cu) for these leaves
+  double *out;              // [n_leaf * P][3] = x + alpha * v on regular points
+  double alpha;
+  unsigned *exc_count;      // exceptions: number and point ids
+  uint32_t *exc_idx;
+};
+
+__device__ __forceinline__ const double *vel_coeff(const TensorParams &p, int j) {
+  return j < p.v_nleaf ? p.vcoeff + (size_t)j * p.vstride
+                       : reinterpret_cast<const double *>(p.ghost + (size_t)(j - p.v_nleaf) * p.ghost_rec + kGhostHdr);
+}
+__device__ __forceinline__ double4 vel_geom(const TensorParams &p, int j) {
+  return j < p.v_nleaf ? p.vgeom[j]
+                       : *reinterpret_cast<const double4 *>(p.ghost + (size_t)(j - p.v_nleaf) * p.ghost_rec + 16);
+}
+__device__ __forceinline__ uint4 vel_box(const TensorParams &p, int j) {
+  return j < p.v_nleaf ? p.vbox[j] : *reinterpret_cast<const uint4 *>(p.ghost + (size_t)(j - p.v_nleaf) * p.ghost_rec);
+}
+
+// this rank's last leaf -> its ghost record (before the all-gather)
+__global__ void ghost_pack_kernel(const uint4 *__restrict__ vbox, const double4 *__restrict__ vgeom,
+                                  const double *__restrict__ vcoeff, int v_nleaf, unsigned vstride, char *rec) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    *reinterpret_cast<uint4 *>(rec) = v_nleaf ? vbox[v_nleaf - 1] : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<double4 *>(rec + 16) = v_nleaf ? vgeom[v_nleaf - 1] : make_double4(0, 0, 0, 2.0);
+    *reinterpret_cast<unsigned long long *>(rec + 48) = (unsigned long long)v_nleaf;
+    *reinterpret_cast<unsigned long long *>(rec + 56) = 0ull;
+  }
+  double *c = reinterpret_cast<double *>(rec + kGhostHdr);
+  for (unsigned e = t; e < vstride; e += blockDim.x) c[e] = v_nleaf ? vcoeff[(size_t)(v_nleaf - 1) * vstride + e] : 0.0;
+}
+
+// grid leaf -> velocity leaf that contains its box (local index, or v_nleaf + r for the ghost of rank r), or -1
 __global__ void grid_leaf_map_kernel(const uint4 *__restrict__ gbox, size_t n_leaf,
                                      const uint64_t *__restrict__ vkeys, const uint4 *__restrict__ vbox,
                                      const uint32_t *__restrict__ vcell, int vshift, int v_nleaf,
-                                     int32_t *__restrict__ map) {
+                                     int32_t *__restrict__ map, const char *__restrict__ ghost, size_t ghost_rec,
+                                     int nranks, int me) {
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_leaf) return;
   const uint4 b = gbox[c];
@@ -69,27 +125,17 @@ __global__ void grid_leaf_map_kernel(const uint4 *__restrict__ gbox, size_t n_le
     const uint4 v = __ldg(vbox + j);
     if (b.w <= v.w && ((((b.x ^ v.x) | (b.y ^ v.y) | (b.z ^ v.z)) >> v.w) == 0u)) r = j;
   }
+  if (r < 0 && ghost) {
+    for (int g = 0; g < nranks; g++) {
+      if (g == me) continue;
+      const char *rec = ghost + (size_t)g * ghost_rec;
+      if (*reinterpret_cast<const unsigned long long *>(rec + 48) == 0ull) continue;  // that rank holds no leaf
+      const uint4 v = *reinterpret_cast<const uint4 *>(rec);
+      if (b.w <= v.w && ((((b.x ^ v.x) | (b.y ^ v.y) | (b.z ^ v.z)) >> v.w) == 0u)) r = v_nleaf + g;
+    }
+  }
   map[c] = r;
 }
-
-struct TensorParams {
-  const double *vcoeff;     // velocity coefficients, [leaf][dof][ncoef_pad]
-  const double4 *vgeom;
-  const uint4 *vbox;
-  unsigned vstride, ncoef_pad;
-  const double4 *ggeom;     // grid tree, already offset to the first leaf of the range
-  const uint8_t *gdepth;
-  const int32_t *map;
-  size_t n_leaf;
-  int d, periodic;
-  const double *x;          // [n_leaf * P][3] the grid points
-  double *xgen;             // != nullptr: the grid points are WRITTEN here first (== x): the kernel is
-                            // also tbslas::CollectChebTreeGridPoints (gridpts.cu) for these leaves
-  double *out;              // [n_leaf * P][3] = x + alpha * v on regular points
-  double alpha;
-  unsigned *exc_count;      // exceptions: number and point ids
-  uint32_t *exc_idx;
-};
 
 __global__ void __launch_bounds__(kTensorThreads)
 tensor_grid_eval_kernel(const TensorParams p, const TensorTables tb_) {
@@ -122,8 +168,8 @@ tensor_grid_eval_kernel(const TensorParams p, const TensorTables tb_) {
     __syncthreads();
     if (j >= 0 && t < 3 * d) {
       const int a = t / d, i = t - a * d;
-      const double4 gc = p.ggeom[leaf], gv = p.vgeom[j];
-      const uint4 vb = p.vbox[j];
+      const double4 gc = p.ggeom[leaf], gv = vel_geom(p, j);
+      const uint4 vb = vel_box(p, j);
       const double len = 1.0 / (double)(1u << p.gdepth[leaf]);
       const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z), vc = a == 0 ? gv.x : (a == 1 ? gv.y : gv.z);
       const unsigned vba = a == 0 ? vb.x : (a == 1 ? vb.y : vb.z);
@@ -153,7 +199,7 @@ tensor_grid_eval_kernel(const TensorParams p, const TensorTables tb_) {
     if (t == 0 && n_reg < (unsigned)P) s_exc_base = atomicAdd(p.exc_count, (unsigned)P - n_reg);
     if (j >= 0 && n_reg) {
       for (int l = 0; l < 3; l++) {
-        const double *C = p.vcoeff + (size_t)j * p.vstride + (size_t)l * p.ncoef_pad;
+        const double *C = vel_coeff(p, j) + (size_t)l * p.ncoef_pad;
         for (int e = t; e < (int)p.ncoef_pad; e += kTensorThreads) sC[e] = C[e];
         __syncthreads();
         // pass 1: rows (i,j) contracted with T_k(x) -- A[row][px]
@@ -243,14 +289,14 @@ tensor_grid_eval_kernel_t(const TensorParams p, const TensorTables tb_) {
     if (t < 3) s_ok[t] = 0u;
     if (t == 0) s_exc_n = 0u;
     if (j >= 0) {  // in flight while the bases are built
-      const double *C = p.vcoeff + (size_t)j * p.vstride;
+      const double *C = vel_coeff(p, j);
       for (int e = t; e < (int)p.vstride; e += kTensorThreads) sC3[e] = C[e];
     }
     __syncthreads();
     if (j >= 0 && t < 3 * D) {
       const int a = t / D, i = t - a * D;
-      const double4 gc = p.ggeom[leaf], gv = p.vgeom[j];
-      const uint4 vb = p.vbox[j];
+      const double4 gc = p.ggeom[leaf], gv = vel_geom(p, j);
+      const uint4 vb = vel_box(p, j);
       const double len = 1.0 / (double)(1u << p.gdepth[leaf]);
       const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z), vc = a == 0 ? gv.x : (a == 1 ? gv.y : gv.z);
       const unsigned vba = a == 0 ? vb.x : (a == 1 ? vb.y : vb.z);
@@ -427,14 +473,14 @@ tensor_grid_dmma_kernel(const TensorParams p, const TensorTables tb_) {
     if (t == 0) s_exc_n = 0u;
     for (int e = t; e < 3 * 256; e += kTensorThreads) sT[e] = 0.0;
     if (j >= 0) {
-      const double *C = p.vcoeff + (size_t)j * p.vstride;
+      const double *C = vel_coeff(p, j);
       for (int e = t; e < (int)p.vstride; e += kTensorThreads) sC3[e] = C[e];
     }
     __syncthreads();
     if (j >= 0 && t < 3 * D) {
       const int a = t / D, i = t - a * D;
-      const double4 gv = p.vgeom[j];
-      const uint4 vb = p.vbox[j];
+      const double4 gv = vel_geom(p, j);
+      const uint4 vb = vel_box(p, j);
       const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z), vc = a == 0 ? gv.x : (a == 1 ? gv.y : gv.z);
       const unsigned vba = a == 0 ? vb.x : (a == 1 ? vb.y : vb.z);
       const double x = __dadd_rn(c, __dmul_rn(glen, tb_.node[i]));            // gridpts.cu
@@ -591,6 +637,7 @@ __global__ void scatter_update_kernel(const double *__restrict__ pos, const doub
 // multi-rank context that decision only uses what every rank knows, because the generic pass over the
 // exceptions of a Morton-sharded velocity tree is a collective evaluation.
 int eval_tree_dev_points(tbslas_tree *t, int bc, double *pos, size_t n, double *out);  // api.cu
+int comm_allgather_bytes(tbslas_ctx *ctx, const void *mine, void *all, size_t bytes);       // comm.cu
 
 void make_grid_base(const tbslas_tree *grid, size_t leaf0, int bc, GridBase *gb) {
   const int d = grid->q + 1;
@@ -618,6 +665,20 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
   const int periodic = (bc == TBSLAS_PERIODIC);
   void *exc_idx = nullptr, *misc = nullptr;
   unsigned *exc_count = nullptr;
+  // Morton-sharded velocity tree: every rank's last leaf, all-gathered (see TensorParams)
+  const char *ghost = nullptr;
+  const size_t ghost_rec = kGhostHdr + sizeof(double) * vel->stride;
+  if (collective) {
+    void *g;
+    TB_TRY(ws_get(ctx, WS_GHOST, ghost_rec * (ctx->nranks + 1), &g));
+    char *mine = (char *)g + ghost_rec * ctx->nranks;
+    StageScope sc(ctx, ST_EXCHANGE, (double)(ghost_rec * ctx->nranks), 1);
+    ghost_pack_kernel<<<1, 256, 0, ctx->stream>>>(vel->d_box, vel->d_geom, vel->d_coeff, (int)vel->n_leaf,
+                                                 (unsigned)vel->stride, mine);
+    TB_CUDA(ctx, cudaGetLastError());
+    TB_TRY(comm_allgather_bytes(ctx, mine, g, ghost_rec));
+    ghost = (const char *)g;
+  }
   if (n) {
     TensorTables tt;
     new_nodes_host(vel->q, tt.node);
@@ -642,12 +703,15 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
     TB_CUDA(ctx, cudaMemsetAsync(exc_count, 0, sizeof(unsigned), ctx->stream));
     grid_leaf_map_kernel<<<(unsigned)((n_leaf + 255) / 256), 256, 0, ctx->stream>>>(
         grid->d_box + leaf0, n_leaf, vel->d_key, vel->d_box, vel->d_cell, vel->cell_shift, (int)vel->n_leaf,
-        (int32_t *)map);
+        (int32_t *)map, ghost, ghost_rec, ctx->nranks, ctx->rank);
     TB_CUDA(ctx, cudaGetLastError());
     TensorParams p;
     p.vcoeff = vel->d_coeff;
     p.vgeom = vel->d_geom;
     p.vbox = vel->d_box;
+    p.v_nleaf = (int)vel->n_leaf;
+    p.ghost = ghost;
+    p.ghost_rec = ghost_rec;
     p.vstride = (unsigned)vel->stride;
     p.ncoef_pad = (unsigned)(vel->stride / vel->dof);
     p.ggeom = grid->d_geom + leaf0;
@@ -703,7 +767,9 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
   // chunk's values in the pipelined host calls).
   size_t m = 0;
   if (n) {
-    ExcCount key{vel->struct_hash, grid->struct_hash, vel->n_leaf, grid->n_leaf, leaf0, n_leaf, vel->q, periodic, 0};
+    // (global hash: with ghost leaves the exception set also depends on the other ranks' shards)
+    ExcCount key{vel->struct_hash ^ (vel->global_hash * 0x9e3779b97f4a7c15ull), grid->struct_hash, vel->n_leaf,
+                 grid->n_leaf, leaf0, n_leaf, vel->q, periodic, 0};
     ExcCount *hit = nullptr;
     for (ExcCount &e : ctx->exc_cache)
       if (e.vel_hash == key.vel_hash && e.grid_hash == key.grid_hash && e.vel_leaves == key.vel_leaves &&

@@ -159,10 +159,12 @@ def main():
         rtree = ctx.tree(vels[1], replicated=True)
         ctx.set_tensor_grid("always")
         solo.set_tensor_grid("always")
+        rep = {}
         for bc in (0, 1):
             a = api.SolveSemilagInSitu(api.NodeFieldFunctor(rtree), tcon, 2, 0.05, 1, bc)
             b = api.SolveSemilagInSitu(api.NodeFieldFunctor(svel[1]), scon, 2, 0.05, 1, bc)
             same("tree-level step (tensor grids) bc%d" % bc, a, b[lo:hi])
+            rep[bc] = a
         # (4d) the tree-level step with a Morton-SHARDED velocity tree (the reference's layout): the first
         # velocity evaluation runs by sum factorisation where the containing velocity leaf is local and
         # through the (collective) generic pass elsewhere; against the single-rank tree-level step
@@ -171,6 +173,9 @@ def main():
             a, da = api.SolveSemilagInSitu(api.NodeFieldFunctor(tvel[1]), tcon, 2, 0.05, 1, bc, departure_points=True)
             b = api.SolveSemilagInSitu(api.NodeFieldFunctor(svel[1]), scon, 2, 0.05, 1, bc)
             close("sharded-velocity tree-level step vs one GPU bc%d" % bc, a, b[lo:hi])
+            # with the ranks' last velocity leaves as ghosts the sum-factorised path covers the very leaves it
+            # covers when the velocity tree is held whole: the two layouts agree bit for bit
+            same("sharded == replicated velocity, tree-level step bc%d" % bc, a, rep[bc])
             if arr.shape[0]:
                 close("ORACLE departure points, sharded tree-level step bc%d" % bc, da,
                       port.traj_rk2(hvel1, arr, 2 * 0.05, 0.05, 1, bc), tol=1e-12 / max(np.abs(da).max(), 1.0))
@@ -234,6 +239,22 @@ def main():
     a = api.SolveSemilagInSitu(api.NodeFieldFunctor(rtree), tcon, 2, 0.05, 1, 0)
     b = api.SolveSemilagInSitu(api.NodeFieldFunctor(svel[1]), scon, 2, 0.05, 1, 0)
     same2("after reshard: tree-level step", a, b[lo_l * Pn:hi_l * Pn])
+    # (7) a mailbox too small for the outsiders: every rank gets TBSLAS_ERR_COMM at the synchronising call
+    # (nothing is written past a peer's buffer, nothing hangs), and the next evaluation works again
+    if "peer" in modes and world > 1:
+        from tbslas_b200.capi import TbslasError
+        ctx.comm_set_exchange("peer")
+        ctx.comm_set_mailbox(64)
+        raised = False
+        try:
+            api.NodeFieldFunctor(tcon)(pts.copy(), bc=0)
+        except TbslasError as e:
+            raised = "mailbox" in str(e)
+        checks.append(("mailbox overflow is an error, not a hang", raised))
+        ctx.comm_set_mailbox(1 << 20)
+        same2("after the overflow: eval works again", api.NodeFieldFunctor(tcon)(pts.copy(), bc=0),
+              api.NodeFieldFunctor(scon)(pts.copy(), bc=0))
+
     ok = all(c[1] for c in checks)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
