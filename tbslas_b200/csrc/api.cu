@@ -188,7 +188,7 @@ static int eval_local_points(tbslas_tree *t, int bc, double *pos, size_t n, int 
     TB_TRY(ws_get(ctx, WS_SENDIDX, sizeof(uint32_t) * (n + 1), &send_idx));
   }
 
-  static const bool exchange_first = !(getenv("TBSLAS_EXCHANGE_FIRST") && atoi(getenv("TBSLAS_EXCHANGE_FIRST")) == 0);
+  const bool exchange_first = ctx->opt.exchange_first;
   const bool reuse = !multi && !leaf_out && !n_dev && same_leaves(t, same_as) &&
                      !(same_as->ctx->nranks > 1 && !same_as->replicated);
   if (reuse) {  // the persistent evaluation kernel's work counter is the one thing to reset
@@ -783,6 +783,19 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TBSLAS_ERR_CUDA;
   if (prop.major != 10) return TBSLAS_ERR_CUDA;  // sm_100a kernels only; no fallback
   tbslas_ctx *ctx = new tbslas_ctx();
+  {  // A/B switches: the environment is read here and nowhere else
+    auto flag = [](const char *name, bool dflt) {
+      const char *e = getenv(name);
+      return e ? atoi(e) != 0 : dflt;
+    };
+    ctx->opt.exchange_first = flag("TBSLAS_EXCHANGE_FIRST", true);
+    ctx->opt.locate_no_boxes = flag("TBSLAS_LOCATE_NO_BOXES", false);
+    ctx->opt.tensor_generic = flag("TBSLAS_TENSOR_GENERIC", false);
+    ctx->opt.tensor_dmma = flag("TBSLAS_TENSOR_DMMA", true);
+    if (const char *e = getenv("TBSLAS_EVAL_VARIANT")) ctx->opt.eval_variant = atoi(e);
+    if (const char *e = getenv("TBSLAS_EXCHANGE")) ctx->opt.peer_exchange = strcmp(e, "nccl") != 0;
+    if (const char *e = getenv("TBSLAS_MAILBOX_POINTS")) ctx->opt.mailbox_points = (size_t)strtoull(e, nullptr, 10);
+  }
   ctx->device = device;
   ctx->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {

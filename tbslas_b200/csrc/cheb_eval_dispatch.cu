@@ -3,8 +3,6 @@
 // cheb_eval_inst_*.cu) whenever one coefficient buffer per warp fits in shared memory at two
 // CTAs per SM; otherwise -- degrees 15..TBSLAS_MAX_CHEB_DEG, or very wide dof -- the
 // degree-generic kernel (cheb_eval_generic.cu).
-#include <cstdlib>
-
 #include "cheb_eval_wt.cuh"
 
 namespace tb {
@@ -20,28 +18,22 @@ constexpr int kMaxUnrolledDeg = 14;  // beyond this nvcc stops unrolling: generi
 constexpr size_t kWtSmemLimit = 27 * 1024;  // eight one-warp CTAs per SM must fit in 227 KB
 int launch_cheb_eval_generic(tbslas_ctx *ctx, const EvalArgs &a);
 
-static int eval_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("TBSLAS_EVAL_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 // 0: warp-pipelined kernel, 1: one-tile-per-CTA kernel, 2: generic kernel
-static int eval_kind(int q, size_t stride) {
+// (variant: the context's A/B switch, TBSLAS_EVAL_VARIANT read once at tbslas_b200_init)
+static int eval_kind(const tbslas_tree *t) {
+  const int q = t->q, variant = t->ctx->opt.eval_variant;
+  const size_t stride = t->stride;
   if (q < 1 || q > TBSLAS_MAX_CHEB_DEG) return -1;
   if (q > kMaxUnrolledDeg) return 2;
-  if (eval_variant() == 1 && (q == 8 || q == 14)) return 1;
-  if (eval_variant() == 2) return 2;
+  if (variant == 1 && (q == 8 || q == 14)) return 1;
+  if (variant == 2) return 2;
   // (13 * 32 * PPT: the largest staging area, that of the grid-base epilogue)
   const size_t smem = (stride + 13 * 32 * (size_t)eval_ppt(q) + 16) * sizeof(double);
   return smem <= kWtSmemLimit ? 0 : 2;
 }
 
 int eval_tile_points(const tbslas_tree *t) {
-  switch (eval_kind(t->q, t->stride)) {
+  switch (eval_kind(t)) {
     case 0: return 32 * eval_ppt(t->q);
     case 1: return kEvalThreads * eval_ppt(t->q);
     case 2: return kEvalThreads;
@@ -49,12 +41,12 @@ int eval_tile_points(const tbslas_tree *t) {
   }
 }
 
-bool eval_needs_tile_map(const tbslas_tree *t) { return eval_kind(t->q, t->stride) != 0; }
-bool eval_supports_grid_base(const tbslas_tree *t) { return eval_kind(t->q, t->stride) == 0 && t->dof == 3; }
+bool eval_needs_tile_map(const tbslas_tree *t) { return eval_kind(t) != 0; }
+bool eval_supports_grid_base(const tbslas_tree *t) { return eval_kind(t) == 0 && t->dof == 3; }
 
 int launch_cheb_eval(tbslas_ctx *ctx, const EvalArgs &a) {
   StageScope sc(ctx, ST_CHEB_EVAL, (double)a.n, 1);
-  const int kind = eval_kind(a.tree->q, a.tree->stride);
+  const int kind = eval_kind(a.tree);
   if (a.epilogue == EPI_AXPY_GRID && kind != 0)
     return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "grid-base epilogue needs the persistent evaluation kernel");
   if (kind == 2) return launch_cheb_eval_generic(ctx, a);

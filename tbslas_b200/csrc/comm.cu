@@ -534,7 +534,7 @@ static void px_teardown(tbslas_ctx *ctx) {
 int px_setup(tbslas_ctx *ctx, size_t cap) {
   ExchangeState &x = xs_of(ctx);
   const int np = ctx->nranks, me = ctx->rank;
-  static const bool disabled = getenv("TBSLAS_EXCHANGE") && !strcmp(getenv("TBSLAS_EXCHANGE"), "nccl");
+  const bool disabled = !ctx->opt.peer_exchange;
   TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   px_teardown(ctx);
   void *buf;
@@ -866,9 +866,7 @@ int tbslas_b200_comm_init(tbslas_ctx *ctx, int nranks, int rank, const void *id1
     TB_CUDA(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   // peer-memory mailboxes (the default exchange where every rank can map every peer; otherwise,
   // on every rank alike, the NCCL all-to-all-v)
-  size_t cap = (size_t)4 << 20;
-  if (const char *e = getenv("TBSLAS_MAILBOX_POINTS")) cap = (size_t)strtoull(e, nullptr, 10);
-  if (nranks > 1) TB_TRY(px_setup(ctx, cap));
+  if (nranks > 1) TB_TRY(px_setup(ctx, ctx->opt.mailbox_points));
   return TBSLAS_OK;
 }
 

@@ -157,6 +157,16 @@ struct tbslas_ctx {
   // multi-rank: state of the exchange in flight (one per context; comm.cu)
   tb::ExchangeState *xs = nullptr;
   int exchange_mode = 1;  // 1: peer-memory mailboxes where available, 0: NCCL all-to-all-v
+  // A/B switches of the kernels, read from the environment ONCE, at tbslas_b200_init, into the context
+  // (no process-global state in the hot functions): TBSLAS_EXCHANGE_FIRST=0, TBSLAS_LOCATE_NO_BOXES=1,
+  // TBSLAS_TENSOR_GENERIC=1, TBSLAS_TENSOR_DMMA=0, TBSLAS_EVAL_VARIANT=1|2, TBSLAS_EXCHANGE=nccl,
+  // TBSLAS_MAILBOX_POINTS=<n>
+  struct Options {
+    bool exchange_first = true, locate_no_boxes = false, tensor_generic = false, tensor_dmma = true;
+    bool peer_exchange = true;
+    int eval_variant = 0;
+    size_t mailbox_points = (size_t)4 << 20;
+  } opt;
 };
 
 struct tbslas_tree {

@@ -271,8 +271,7 @@ int launch_locate(tbslas_ctx *ctx, const LocateArgs &a) {
   if (a.n == 0) return TBSLAS_OK;
   const size_t per_cta = (size_t)kLocateThreads * kLocItems;
   const unsigned grid = (unsigned)((a.n + per_cta - 1) / per_cta);
-  static const bool no_boxes = getenv("TBSLAS_LOCATE_NO_BOXES") && atoi(getenv("TBSLAS_LOCATE_NO_BOXES"));
-  const bool boxes = t->boxes_ok && !no_boxes;
+  const bool boxes = t->boxes_ok && !ctx->opt.locate_no_boxes;
   if (multi && a.send_count != a.count + t->n_leaf + 2)
     return fail(ctx, TBSLAS_ERR_INVALID, "send counts must follow the leaf bins");
 #define TB_LOCATE(M, B)                                                                          \

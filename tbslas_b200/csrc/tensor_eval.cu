@@ -726,8 +726,8 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
     p.alpha = alpha;
     p.exc_count = exc_count;
     p.exc_idx = (uint32_t *)exc_idx;
-    static const bool force_generic = getenv("TBSLAS_TENSOR_GENERIC") && atoi(getenv("TBSLAS_TENSOR_GENERIC"));
-    static const int dmma_mode = getenv("TBSLAS_TENSOR_DMMA") ? atoi(getenv("TBSLAS_TENSOR_DMMA")) : 1;
+    const bool force_generic = ctx->opt.tensor_generic;
+    const bool dmma_mode = ctx->opt.tensor_dmma;
     bool launched = false;
     if (!force_generic && dmma_mode) {
       switch (d) {
