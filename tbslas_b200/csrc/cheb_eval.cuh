@@ -105,6 +105,13 @@ __device__ __forceinline__ void cheb_basis(double xi, double (&T)[Q + 1]) {
 //
 // Rows (i,j) and (i,j+1) are contracted together so a thread always has 2*PPT independent
 // DFMA chains in flight (DFMA latency 8 cycles, issue interval 2).
+struct CoefG4 { const double *p; };  // 32-byte aligned coefficient block in global memory
+struct CoefReg { double a, b; };     // no loads at all (ceiling of the contraction)
+#ifdef TB_EVALBENCH_CONST  // tools/evalbench.cu only
+__constant__ double g_coef_const[2 * 1024];
+template <int B> struct CoefConst {};  // constant bank at a compile-time offset: the DFMA's own operand
+#endif
+
 template <int Q, int PPT, bool PYS, bool PAIR, int I, int J, int CI>
 struct RowPair {
   static constexpr int D = Q + 1;
@@ -115,6 +122,18 @@ struct RowPair {
     return (i & 1) ? C2[i >> 1].y : C2[i >> 1].x;
   }
   static __device__ __forceinline__ double coef(const double *C1, int i) { return C1[i]; }
+  // experiments (tools/evalbench.cu): coefficients by 256-bit broadcast loads from global memory through
+  // L1 (four per instruction; identical loads of one quad are merged by the compiler), or from registers
+  static __device__ __forceinline__ double coef(CoefG4 c, int i) {
+    double q0, q1, q2, q3;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q0), "=d"(q1), "=d"(q2), "=d"(q3) : "l"(c.p + (i & ~3)));
+    return (i & 3) == 0 ? q0 : ((i & 3) == 1 ? q1 : ((i & 3) == 2 ? q2 : q3));
+  }
+  static __device__ __forceinline__ double coef(CoefReg c, int i) { return (i & 1) ? c.b : c.a; }
+#ifdef TB_EVALBENCH_CONST
+  template <int B>
+  static __device__ __forceinline__ double coef(CoefConst<B>, int i) { return g_coef_const[B + i]; }
+#endif
   template <class CP>
   static __device__ __forceinline__ void run(CP C2,
                                              const double (&px)[PPT][D],

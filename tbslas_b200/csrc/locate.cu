@@ -25,6 +25,9 @@ constexpr int kLocateThreads = 256;
 // atomic per (CTA, distinct bin) instead of one per warp: departure points of one source
 // leaf land in a handful of leaves, and thousands of same-address L2 atomics serialise.
 constexpr int kLocItems = 8;
+#ifndef TB_LOCATE_GUESSES
+#define TB_LOCATE_GUESSES 1  // leaves a warp remembers between batches (2 measured on C2: 4.81 ms against 4.77, the kernel is issue bound)
+#endif
 constexpr int kLocTable = 64;  // distinct bins a CTA can aggregate; overflow -> direct atomics
 
 __device__ __forceinline__ int table_slot(int *s_bin, int bin) {
@@ -74,9 +77,12 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
   // per point: (row of the CTA table + 1) << 24 | rank inside that row, completed with the
   // row's global base once the whole CTA has counted (row 0: the rank is final already)
   __shared__ uint32_t s_rec[kLocItems][kLocateThreads];
-  int guess = -1;  // leaf the previous batch of this warp resolved to (warp-uniform)
-  uint4 gbox = make_uint4(0, 0, 0, 0);  // its integer box
-  int gslot = -2;                       // its row of the CTA table (-2: not looked up yet)
+  // the two leaves the previous batches of this warp resolved most lanes to (warp-uniform): a warp's 32
+  // consecutive departure points usually straddle two leaves, and one remembered leaf sent the lanes
+  // of the other through the key search in every batch
+  int guess = -1, guess2 = -1;
+  uint4 gbox = make_uint4(0, 0, 0, 0), gbox2 = make_uint4(0, 0, 0, 0);  // their integer boxes
+  int gslot = -2, gslot2 = -2;  // their rows of the CTA table (-2: not looked up yet)
 
   auto claim = [&](int bin, unsigned m, int leader, int &slot, uint32_t &base) {
     // one table (or, on overflow, global) update for the lanes in m, all in `bin`
@@ -137,31 +143,33 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
     uint32_t rank = 0;
     bool todo = valid;
 
-    int n_hit = 0;  // lanes the remembered leaf resolved
-    if (BOXES && guess >= 0) {  // warp-uniform
-      const bool hit = todo && in && ((((ix ^ gbox.x) | (iy ^ gbox.y) | (iz ^ gbox.z)) >> gbox.w) == 0u);
+    // lanes inside the box of a remembered leaf g: one aggregated table update, no key, no search
+    auto try_guess = [&](int g, const uint4 &gb, int &gs) -> int {
+      const bool hit = todo && in && ((((ix ^ gb.x) | (iy ^ gb.y) | (iz ^ gb.z)) >> gb.w) == 0u);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
-      n_hit = __popc(m);
       if (m) {
         const int claimer = __ffs(m) - 1;
-        if (gslot == -2) {  // first hit on this guess: find its row of the CTA table once
+        if (gs == -2) {  // first hit on this guess: find its row of the CTA table once
           int sl = -1;
-          if (lane == claimer) sl = table_slot(s_bin, guess);
-          gslot = __shfl_sync(0xffffffffu, sl, claimer);
+          if (lane == claimer) sl = table_slot(s_bin, g);
+          gs = __shfl_sync(0xffffffffu, sl, claimer);
         }
         uint32_t base = 0;
         if (lane == claimer)
-          base = (gslot >= 0) ? atomicAdd(s_cnt + gslot, (unsigned)__popc(m))
-                              : atomicAdd(count + guess, (unsigned)__popc(m));
+          base = (gs >= 0) ? atomicAdd(s_cnt + gs, (unsigned)__popc(m)) : atomicAdd(count + g, (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, claimer);
         if (hit) {
-          bin = guess;
-          slot = gslot;
+          bin = g;
+          slot = gs;
           rank = base + __popc(m & lt);
           todo = false;
         }
       }
-    }
+      return __popc(m);
+    };
+    int n_hit = 0, n_hit2 = 0;  // lanes the remembered leaves resolved
+    if (BOXES && guess >= 0) n_hit = try_guess(guess, gbox, gslot);                    // warp-uniform conditions
+    if (BOXES && TB_LOCATE_GUESSES > 1 && guess2 >= 0) n_hit2 = try_guess(guess2, gbox2, gslot2);
 
     if (__any_sync(0xffffffffu, todo)) {  // slow path: keys, owners, searches
       const uint64_t key = in ? anchor_key(ix, iy, iz) : ~0ull;
@@ -230,10 +238,18 @@ locate_kernel(const uint64_t *__restrict__ keys, const uint4 *__restrict__ boxes
         rank = __shfl_sync(peers, base, leader) + __popc(peers & lt);
         n_new = (j >= 0) ? __popc(peers) : 0;
       }
-      // the leaf that took the most lanes becomes the next batch's guess, unless the old guess
-      // still holds more of the warp
+      // the leaf that took the most lanes replaces the remembered leaf that resolved fewer lanes of
+      // this batch, unless that one still holds more of the warp (a lane a remembered leaf contains
+      // never reaches the search, so the new leaf differs from both)
       const unsigned best = __reduce_max_sync(0xffffffffu, ((unsigned)n_new << 8) | (unsigned)(31 - lane));
-      if ((int)(best >> 8) > n_hit) {
+      const int n_best = (int)(best >> 8);
+      if (TB_LOCATE_GUESSES > 1 && (guess2 < 0 || n_hit2 < n_hit) && guess >= 0) {
+        if (n_best > n_hit2) {
+          guess2 = __shfl_sync(0xffffffffu, bin, 31 - (int)(best & 0xffu));
+          gslot2 = -2;
+          if (BOXES) gbox2 = __ldg(boxes + guess2);
+        }
+      } else if (n_best > n_hit) {
         guess = __shfl_sync(0xffffffffu, bin, 31 - (int)(best & 0xffu));
         gslot = -2;
         if (BOXES) gbox = __ldg(boxes + guess);
@@ -380,8 +396,15 @@ __global__ void tile_map_kernel(const uint32_t *__restrict__ bin_start,
 // (nranks <= 64).  MODE 2 (peer exchange): the coordinates go straight into the owner's receive
 // buffer over NVLink peer memory, at the place comm.cu's px_offsets_kernel derived from the count
 // matrix; only the origin index stays here (bucket order, for the unpack).
+constexpr int kScatterThreads = 256;
+#ifndef TB_SCATTER_ITEMS
+#define TB_SCATTER_ITEMS 4
+#endif
+constexpr int kScatterItems = TB_SCATTER_ITEMS;
+
 template <int MODE>
-__global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint32_t *__restrict__ rank,
+__global__ void __launch_bounds__(kScatterThreads)
+scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint32_t *__restrict__ rank,
                                     const uint32_t *__restrict__ bin_start, size_t n,
                                     const uint32_t *__restrict__ n_dev,
                                     uint32_t *__restrict__ perm, const double *__restrict__ pos,
@@ -413,25 +436,42 @@ __global__ void scatter_perm_kernel(const int32_t *__restrict__ leaf, const uint
     const size_t nd = *n_dev;
     n = nd < n ? nd : n;
   }
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int j = leaf[i];
-  if (j >= 0) {
-    perm[__ldg(bin_start + j) + rank[i]] = (uint32_t)i;
-  } else if (MODE == 1) {  // travels to its owner
-    const unsigned slot = s_off[-2 - j] + rank[i];
-    send_pos[3 * (size_t)slot] = pos[3 * i];
-    send_pos[3 * (size_t)slot + 1] = pos[3 * i + 1];
-    send_pos[3 * (size_t)slot + 2] = pos[3 * i + 2];
-    send_idx[slot] = (uint32_t)i;
-  } else if (MODE == 2 && !s_skip) {
-    const int o = -2 - j;
-    const unsigned r = rank[i];
-    double *dst = reinterpret_cast<double *>(px.peer_base[o] + px.off_recv_pos) + 3 * ((size_t)s_dst[o] + r);
-    dst[0] = pos[3 * i];
-    dst[1] = pos[3 * i + 1];
-    dst[2] = pos[3 * i + 2];
-    send_idx[s_off[o] + r] = (uint32_t)i;
+  // kScatterItems points per thread, all (leaf, rank) loads issued before the first dependent
+  // bin_start load: the pass is pure latency otherwise (one point per thread ran at 2.6 TB/s)
+  const size_t i0 = (size_t)blockIdx.x * (kScatterThreads * kScatterItems) + threadIdx.x;
+  int jv[kScatterItems];
+  uint32_t rv[kScatterItems];
+#pragma unroll
+  for (int k = 0; k < kScatterItems; k++) {
+    const size_t i = i0 + (size_t)k * kScatterThreads;
+    jv[k] = i < n ? leaf[i] : 0;
+    rv[k] = i < n ? rank[i] : 0u;
+  }
+  uint32_t bs[kScatterItems];
+#pragma unroll
+  for (int k = 0; k < kScatterItems; k++) bs[k] = jv[k] >= 0 ? __ldg(bin_start + jv[k]) : 0u;
+#pragma unroll
+  for (int k = 0; k < kScatterItems; k++) {
+    const size_t i = i0 + (size_t)k * kScatterThreads;
+    if (i >= n) break;
+    const int j = jv[k];
+    if (j >= 0) {
+      perm[bs[k] + rv[k]] = (uint32_t)i;
+    } else if (MODE == 1) {  // travels to its owner
+      const unsigned slot = s_off[-2 - j] + rv[k];
+      send_pos[3 * (size_t)slot] = pos[3 * i];
+      send_pos[3 * (size_t)slot + 1] = pos[3 * i + 1];
+      send_pos[3 * (size_t)slot + 2] = pos[3 * i + 2];
+      send_idx[slot] = (uint32_t)i;
+    } else if (MODE == 2 && !s_skip) {
+      const int o = -2 - j;
+      const unsigned r = rv[k];
+      double *dst = reinterpret_cast<double *>(px.peer_base[o] + px.off_recv_pos) + 3 * ((size_t)s_dst[o] + r);
+      dst[0] = pos[3 * i];
+      dst[1] = pos[3 * i + 1];
+      dst[2] = pos[3 * i + 2];
+      send_idx[s_off[o] + r] = (uint32_t)i;
+    }
   }
 }
 
@@ -447,7 +487,8 @@ int launch_bin(tbslas_ctx *ctx, const BinArgs &a) {
     TB_CUDA(ctx, cudaGetLastError());
   }
   if (a.n) {
-    const unsigned grid = (unsigned)((a.n + 255) / 256);
+    const size_t per_cta = (size_t)kScatterThreads * kScatterItems;
+    const unsigned grid = (unsigned)((a.n + per_cta - 1) / per_cta);
     if (a.px)
       scatter_perm_kernel<2><<<grid, 256, 0, ctx->stream>>>(a.leaf, a.rank, a.bin_start, a.n, a.n_dev, a.perm,
                                                           a.pos, a.send_count, a.nranks, nullptr, a.send_idx,

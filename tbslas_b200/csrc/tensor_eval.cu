@@ -24,6 +24,7 @@
 #include <cstring>
 #include <vector>
 
+#include "cheb_eval.cuh"  // mbarrier / bulk-TMA helpers
 #include "common.cuh"
 #include "gridbase.cuh"
 #include "keys.cuh"
@@ -33,6 +34,14 @@ namespace tb {
 constexpr int kTensorThreads = 256;
 #ifndef TB_TENSOR_MINB
 #define TB_TENSOR_MINB 2
+#endif
+#ifndef TB_TENSOR_XSTORE_CS
+#define TB_TENSOR_XSTORE_CS 0  // 1: arrival points by streaming stores (st.global.cs)
+#endif
+#if TB_TENSOR_XSTORE_CS
+#define TB_TENSOR_XSTORE(ptr, v) __stcs((ptr), (v))
+#else
+#define TB_TENSOR_XSTORE(ptr, v) (*(ptr) = (v))
 #endif
 constexpr int kMaxD = TBSLAS_MAX_CHEB_DEG + 1;
 constexpr int kMaxRows = kMaxD * (kMaxD + 1) / 2;
@@ -595,6 +604,257 @@ static int launch_tensor_dmma(tbslas_ctx *ctx, const TensorParams &p, const Tens
   return TBSLAS_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Second DMMA kernel (round 2, the default): the same three GEMM passes and the same values, with the
+// per-leaf work AROUND the GEMMs taken off the critical path.  ncu of the first version showed 4 % FP64
+// and 46 % issue utilisation with 82 k SM-clocks per three leaves: the time went into (a) the arrival-point
+// loop (four integer divisions and a lane-divergent constant-bank load per element), (b) lane-divergent
+// constant-bank loads of the row tables and nodes inside the passes (an LDC with different indices in a
+// warp is replayed per distinct index), (c) a synchronous 16 KB coefficient copy per leaf, (d) k-step loops
+// of data-dependent length whose loads were issued one DMMA at a time.  Here:
+//   * tables (nodes, row offsets/lengths) live in shared memory, filled once per CTA;
+//   * the coordinates of the leaf's grid are 3 x D numbers (sX) computed once per leaf by the threads that
+//     build the bases; the arrival points are a table expansion with per-thread selectors fixed for the
+//     whole launch (no division per element), and the epilogue takes its base coordinate from sX too
+//     (same expression, same bits);
+//   * the NEXT leaf's coefficient block arrives by one bulk-TMA copy (cp.async.bulk + mbarrier), issued
+//     as soon as the last component's pass 1 has consumed the current block: no copy loop, no latency;
+//   * the k-steps of passes 1 and 2 are unrolled: all fragment loads first, then the DMMAs;
+//   * persistent CTAs (3 per SM), one barrier less per leaf (exception counters double buffered).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_cta() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int D>
+__global__ void __launch_bounds__(kTensorThreads, 3)
+tensor_grid_dmma2_kernel(const TensorParams p, const TensorTables tb_) {
+  constexpr int P2 = D * D, P = P2 * D, NROW = D * (D + 1) / 2, MT1 = (NROW + 7) / 8, KS = (D + 3) / 4;
+  constexpr int XG = (3 * P2 + kTensorThreads - 1) / kTensorThreads;  // arrival-point slots per thread and z-plane
+  static_assert(D <= 16, "one 16-wide tile per axis");
+  extern __shared__ __align__(16) double sm[];
+  double *sT = sm;                    // [3][16][16]  T_deg(point) per axis, degree major, zero padded
+  double *sC3 = sT + 3 * 256;         // [3][ncoef_pad]  (bulk-TMA destination, 16-byte aligned)
+  double *sA1 = sC3 + p.vstride;      // [MT1*8][16]
+  double *sB2 = sA1 + MT1 * 8 * 16;   // [16][16][16]  (plane, py, px)
+  __shared__ double sX[3 * 16];       // coordinates of the leaf's grid, per axis
+  __shared__ double sNode[16];
+  __shared__ uint32_t sRow[MT1 * 8];  // row (i,j): first coefficient | length << 16
+  __shared__ unsigned s_ok[2][4];     // [leaf parity][axis]
+  __shared__ unsigned s_exc[2][2];    // [leaf parity]{base, n}
+  __shared__ __align__(8) uint64_t s_bar;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int lr = lane >> 2, lc = lane & 3;  // fragment row / column index of this lane
+  for (int e = D * 256 + t; e < 16 * 256; e += kTensorThreads) sB2[e] = 0.0;  // planes >= D stay zero (pass 2 writes whole planes < D)
+  for (int e = t; e < 3 * 256; e += kTensorThreads) sT[e] = 0.0;    // degrees / points >= D stay zero
+  if (t < 16) sNode[t] = t < D ? tb_.node[t] : 0.0;
+  if (t < MT1 * 8) sRow[t] = t < NROW ? ((uint32_t)tb_.row_off[t] | ((uint32_t)tb_.row_len[t] << 16)) : 0u;
+  if (t < 8) (&s_ok[0][0])[t] = 0u;
+  if (t < 4) (&s_exc[0][0])[t] = 0u;
+  if (t == 0) mbar_init(&s_bar, 1);
+  // selectors of this thread's arrival-point slots inside one z-plane: element r = 3*(py*D + px) + axis
+  int xsel[XG];  // >= 0: index into sX (x: px, y: 16 + py), -1: the plane's z, -2: no element
+#pragma unroll
+  for (int m = 0; m < XG; m++) {
+    const int r = t + m * kTensorThreads;
+    const int pt = r / 3, a = r - 3 * pt, py = pt / D, px = pt - py * D;
+    xsel[m] = r >= 3 * P2 ? -2 : (a == 0 ? px : (a == 1 ? 16 + py : -1));
+  }
+  __syncthreads();
+  auto fetch_coeff = [&](int jv) {  // one thread: the block of velocity leaf jv -> sC3
+    fence_proxy_async_cta();        // earlier generic-proxy reads of sC3 vs. the async-proxy write
+    const uint32_t bytes = p.vstride * 8u;
+    mbar_expect_tx(&s_bar, bytes);
+    tma_bulk_g2s(sC3, vel_coeff(p, jv), bytes, &s_bar);
+  };
+  uint32_t phase = 0;
+  bool prefetched = false;  // CTA-uniform: this leaf's block was requested during the previous leaf
+  int par = 0;
+  for (size_t leaf = blockIdx.x; leaf < p.n_leaf; leaf += gridDim.x, par ^= 1) {
+    const int j = p.map[leaf];
+    const size_t gp0 = leaf * (size_t)P;
+    const double4 gc = p.ggeom[leaf];
+    const double glen = 1.0 / (double)(1u << p.gdepth[leaf]);
+    __syncthreads();  // the previous leaf's passes are done with sT, sX, sC3
+    if (j >= 0 && !prefetched && t == 0) fetch_coeff(j);
+    if (t < 3 * D) {
+      const int a = t / D, i = t - a * D;
+      const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z);
+      const double x = __dadd_rn(c, __dmul_rn(glen, sNode[i]));  // gridpts.cu
+      sX[a * 16 + i] = x;
+      if (j >= 0) {
+        const double4 gv = vel_geom(p, j);
+        const uint4 vb = vel_box(p, j);
+        const double vc = a == 0 ? gv.x : (a == 1 ? gv.y : gv.z);
+        const unsigned vba = a == 0 ? vb.x : (a == 1 ? vb.y : vb.z);
+        const double xi = __dadd_rn(__dmul_rn(__dsub_rn(x, vc), gv.w), -1.0);  // cheb_eval.cuh
+        const bool in = fabs(xi) <= 1.0;
+        const double xc = in ? xi : 0.0, x2 = 2.0 * xc;
+        double t0 = in ? 1.0 : 0.0, t1 = xc;
+        double *T = sT + a * 256;  // [degree][point], swizzled
+        T[swz(0, i)] = t0;
+        if (D > 1) T[swz(1, i)] = t1;
+#pragma unroll
+        for (int k = 2; k < D; k++) {
+          const double t2 = __dsub_rn(__dmul_rn(x2, t1), t0);
+          T[swz(k, i)] = t2;
+          t0 = t1;
+          t1 = t2;
+        }
+        const double xs = x * 32768.0;
+        int jx = __double2int_rd(xs);
+        if (!p.periodic && xs == 32768.0) jx = 32767;
+        if ((unsigned)jx < 32768u && ((((unsigned)jx ^ vba) >> vb.w) == 0u)) atomicOr(&s_ok[par][a], 1u << i);
+      }
+    }
+    __syncthreads();
+    const unsigned okx = s_ok[par][0], oky = s_ok[par][1], okz = s_ok[par][2];
+    const unsigned n_reg = (unsigned)(__popc(okx) * __popc(oky) * __popc(okz));
+    if (t == 0 && n_reg < (unsigned)P) s_exc[par][0] = atomicAdd(p.exc_count, (unsigned)P - n_reg);
+    if (t < 3) s_ok[par ^ 1][t] = 0u;  // the next leaf's masks and counter (last read before this leaf's first barrier)
+    if (t == 0) s_exc[par ^ 1][1] = 0u;
+    if (p.xgen) {  // arrival points of this leaf: a table expansion, fully coalesced
+      double xv[XG];
+#pragma unroll
+      for (int m = 0; m < XG; m++) xv[m] = xsel[m] >= 0 ? sX[xsel[m]] : 0.0;
+      double *o = p.xgen + 3 * gp0 + t;
+#pragma unroll 5
+      for (int pz = 0; pz < D; pz++) {
+        const double zq = sX[32 + pz];
+#pragma unroll
+        for (int m = 0; m < XG; m++)
+          if (xsel[m] != -2) TB_TENSOR_XSTORE(o + pz * 3 * P2 + m * kTensorThreads, xsel[m] == -1 ? zq : xv[m]);
+      }
+    }
+    if (j >= 0) {  // the coefficient block has landed (waited for even when no pass runs: phases stay in step)
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+    }
+    prefetched = false;
+    if (j >= 0 && n_reg) {
+      // Tz fragments of pass 3 (the same for every column tile and component)
+      double az[2][KS];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) az[mt][ks] = sT[512 + swz(ks * 4 + lc, mt * 8 + lr)];
+      for (int l = 0; l < 3; l++) {
+        const double *C = sC3 + l * p.ncoef_pad;
+        // ---- pass 1: A1[r][px] = sum_k Cpad[r][k] Tx[k][px]
+        // (a warp keeps its column tile: the Tx fragments are loaded once per pass; every fragment address
+        //  is base + 64 * k-step, the swizzle term does not depend on the k-step)
+        {
+          const int nt = warp & 1;
+          const double *pb = sT + lc * 16 + ((nt * 8 + lr) ^ (lc << 2));
+          double b[KS];
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) b[ks] = pb[ks * 64];
+          for (int mt = warp >> 1; mt < MT1; mt += kTensorThreads / 64) {
+            const int r = mt * 8 + lr;
+            const uint32_t rw = sRow[r];
+            const int rlen = (int)(rw >> 16);
+            const double *pa = C + (rw & 0xffffu) + lc;
+            const int nks = (tb_.tile_k[mt] + 3) >> 2;  // warp-uniform index
+            double a[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) a[ks] = ks * 4 + lc < rlen ? pa[ks * 4] : 0.0;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+              if (ks < nks) dmma884(c0, c1, a[ks], b[ks]);
+            *reinterpret_cast<double2 *>(sA1 + swz(r, nt * 8 + 2 * lc)) = make_double2(c0, c1);
+          }
+        }
+        __syncthreads();
+        if (l == 2) {  // sC3 is free: request the next leaf's block now, it lands under passes 2 and 3
+          const size_t next = leaf + gridDim.x;
+          if (next < p.n_leaf) {
+            const int jn = p.map[next];
+            if (jn >= 0 && t == 0) fetch_coeff(jn);
+            prefetched = true;
+          }
+        }
+        // ---- pass 2: B2[i][py][px] = sum_j Ty[j][py] A1[(i,j)][px]
+        // (a warp keeps its output tile (py tile, px tile) and takes every other plane: the Ty fragments
+        //  are loaded once per pass)
+        {
+          const int mt = warp & 1, nt = (warp >> 1) & 1;
+          const double *pa = sT + 256 + lc * 16 + ((mt * 8 + lr) ^ (lc << 2));
+          double a[KS];
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) a[ks] = pa[ks * 64];
+          for (int i = warp >> 2; i < D; i += kTensorThreads / 128) {
+            const int nj = D - i, rb = tb_.row_first[i] + lc;  // warp-uniform index
+            const double *pb = sA1 + rb * 16 + ((nt * 8 + lr) ^ ((rb & 3) << 2));
+            double b[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) b[ks] = ks * 4 + lc < nj ? pb[ks * 64] : 0.0;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+              if (ks * 4 < nj) dmma884(c0, c1, a[ks], b[ks]);
+            *reinterpret_cast<double2 *>(sB2 + i * 256 + (mt * 8 + lr) * 16 + ((nt * 8 + 2 * lc) ^ ((i & 3) << 2))) = make_double2(c0, c1);
+          }
+        }
+        __syncthreads();
+        // ---- pass 3: U[pz][(py,px)] = sum_i Tz[i][pz] B2[i][(py,px)];  x' = x + alpha U on regular points
+        const double *sXl = sX + l * 16;
+        double *const ob = p.out + 3 * gp0 + l;
+        const unsigned okxd = okx & ((1u << D) - 1u), okzd = okz & ((1u << D) - 1u);  // (bits >= D are never set)
+        for (int nt = warp; nt < 2 * D; nt += kTensorThreads / 32) {
+          const int py = nt >> 1, px0 = (nt & 1) * 8 + 2 * lc;
+          if (!((oky >> py) & 1u)) continue;  // warp-uniform: the whole row is exceptions
+          double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          const double *pb = sB2 + lc * 256 + ((nt * 8 + lr) ^ (lc << 2));
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) {
+            const double b = pb[ks * 1024];
+            dmma884(c[0][0], c[0][1], az[0][ks], b);
+            dmma884(c[1][0], c[1][1], az[1][ks], b);
+          }
+          double *o = ob + 3 * (lr * P2 + py * D + px0);
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) {
+            const int pz = mt * 8 + lr;
+            if (!((okzd >> pz) & 1u)) continue;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int px = px0 + h;
+              if (!((okxd >> px) & 1u)) continue;
+              const double x0 = sXl[l == 0 ? px : (l == 1 ? py : pz)];
+              o[mt * (24 * P2) + 3 * h] = __dadd_rn(x0, __dmul_rn(p.alpha, c[mt][h]));  // traj.inc:36
+            }
+          }
+        }
+        // (pass 1 of the next component only writes sA1; its barrier orders pass 2 after this pass 3)
+      }
+    }
+    if (n_reg < (unsigned)P) {  // list the exceptions of this leaf (CTA-uniform condition)
+      __syncthreads();
+      const unsigned base = s_exc[par][0];
+      for (int e = t; e < P; e += kTensorThreads) {
+        const int pz = e / P2, rem = e - pz * P2, py = rem / D, px = rem - py * D;
+        if (j >= 0 && (((okx >> px) & (oky >> py) & (okz >> pz)) & 1u)) continue;
+        const unsigned k = atomicAdd(&s_exc[par][1], 1u);
+        p.exc_idx[base + k] = (uint32_t)(gp0 + e);
+      }
+    }
+  }
+}
+
+template <int D>
+static int launch_tensor_dmma2(tbslas_ctx *ctx, const TensorParams &p, const TensorTables &tt, size_t n_leaf) {
+  constexpr int NROW = D * (D + 1) / 2, MT1 = (NROW + 7) / 8;
+  const size_t smem = sizeof(double) * ((size_t)3 * 256 + p.vstride + (size_t)MT1 * 8 * 16 + 16 * 256);
+  auto k = tensor_grid_dmma2_kernel<D>;
+  TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  const size_t cap = (size_t)ctx->n_sm * (size_t)ctx->opt.tensor_ctas_per_sm;  // persistent: 3 resident CTAs per SM
+  const size_t want = n_leaf < cap ? n_leaf : cap;
+  k<<<(unsigned)want, kTensorThreads, smem, ctx->stream>>>(p, tt);
+  TB_CUDA(ctx, cudaGetLastError());
+  return TBSLAS_OK;
+}
+
 __global__ void publish_count_kernel(const unsigned *__restrict__ src, unsigned *host_word) {
   *reinterpret_cast<volatile unsigned *>(host_word) = *src;
   __threadfence_system();
@@ -727,13 +987,13 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
     p.exc_count = exc_count;
     p.exc_idx = (uint32_t *)exc_idx;
     const bool force_generic = ctx->opt.tensor_generic;
-    const bool dmma_mode = ctx->opt.tensor_dmma;
+    const int dmma_mode = ctx->opt.tensor_dmma;  // 0: scalar kernels, 1: first DMMA kernel, 2: the default
     bool launched = false;
     if (!force_generic && dmma_mode) {
       switch (d) {
 #define TB_CASE(DD) \
   case DD:          \
-    TB_TRY(launch_tensor_dmma<DD>(ctx, p, tt, n_leaf)); \
+    TB_TRY(dmma_mode == 1 ? launch_tensor_dmma<DD>(ctx, p, tt, n_leaf) : launch_tensor_dmma2<DD>(ctx, p, tt, n_leaf)); \
     launched = true; \
     break;
         TB_CASE(9) TB_CASE(10) TB_CASE(11) TB_CASE(12) TB_CASE(13) TB_CASE(14) TB_CASE(15) TB_CASE(16)

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <vector>
 
+#define TB_EVALBENCH_CONST 1
 #include "cheb_eval.cuh"
 
 using namespace tb;
@@ -65,6 +66,80 @@ steady_kernel(const double *__restrict__ coef, unsigned stride, double *__restri
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// the same loop with the coefficients (SRC 1) read by 256-bit broadcast loads from global memory through
+// L1, or (SRC 2) taken from registers: what the contraction does when no load competes with the DFMAs
+template <int Q, int PPT, int SRC, int MINB>
+__global__ void __launch_bounds__(kEvalThreads, MINB)
+steady_src_kernel(const double *__restrict__ coef, unsigned stride, double *__restrict__ out, int iters) {
+  constexpr int D = Q + 1;
+  double px[PPT][D], py[PPT][D], zc[PPT], z0[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; s++) {
+    const double xi = -0.9 + 1.7e-3 * threadIdx.x + 0.11 * s, yi = 0.8 - 2.1e-3 * threadIdx.x - 0.07 * s;
+    cheb_basis<Q>(xi, px[s]);
+    cheb_basis<Q>(yi, py[s]);
+    zc[s] = 0.3 - 1e-3 * threadIdx.x;
+    z0[s] = 1.0;
+  }
+  double acc[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; s++) acc[s] = 0;
+  const unsigned gstride = (stride + 3) & ~3u;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    double u[PPT], tz0[PPT], tz1[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+      u[s] = tz0[s] = tz1[s] = 0.0;
+      px[s][0] += 1e-13;  // every row sum starts from px[0]: nothing of the contraction is loop invariant
+    }
+    if (SRC == 1) {
+      CoefG4 c{coef + (size_t)((it + blockIdx.x) & 7) * gstride};
+      ZLevel<Q, PPT, false, false, 0, 0>::run(c, px, py, nullptr, zc, z0, tz0, tz1, u);
+    } else if (SRC == 3) {  // two blocks, alternating (every DFMA takes its coefficient as a constant-bank operand)
+      if (it & 1)
+        ZLevel<Q, PPT, false, false, 0, 0>::run(CoefConst<1024>(), px, py, nullptr, zc, z0, tz0, tz1, u);
+      else
+        ZLevel<Q, PPT, false, false, 0, 0>::run(CoefConst<0>(), px, py, nullptr, zc, z0, tz0, tz1, u);
+    } else {
+      CoefReg c{1e-3 * it, 0.5 - 1e-3 * it};
+      ZLevel<Q, PPT, false, false, 0, 0>::run(c, px, py, nullptr, zc, z0, tz0, tz1, u);
+    }
+#pragma unroll
+    for (int s = 0; s < PPT; s++) acc[s] += u[s];
+  }
+  double r = 0;
+#pragma unroll
+  for (int s = 0; s < PPT; s++) r += acc[s];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+template <int Q, int PPT, int SRC, int MINB>
+void run_src(const char *name, int ctas_per_sm, int n_sm, const double *d_coef, double *d_out) {
+  constexpr int D = Q + 1;
+  const unsigned ncoef = D * (D + 1) * (D + 2) / 6, stride = ncoef + (ncoef & 1);
+  auto k = steady_src_kernel<Q, PPT, SRC, MINB>;
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, k));
+  const int iters = 400, grid = n_sm * ctas_per_sm;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0));
+    k<<<grid, kEvalThreads>>>(d_coef, stride, d_out, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep && ms < best) best = ms;
+  }
+  const double dfma = (double)(ncoef + D * (D + 1) / 2 + D) * PPT * kEvalThreads * (double)grid * iters;
+  printf("%-28s q=%d ppt=%d src=%d regs=%3d ctas/sm=%d : %.3f ms  %.2f TFLOP/s (executed DFMA)\n", name, Q, PPT,
+         SRC, fa.numRegs, ctas_per_sm, best, 2 * dfma / best * 1e-9);
+}
+
 template <int Q, int PPT, bool PYS, bool PAIR, int MINB>
 void run(const char *name, int ctas_per_sm, int n_sm, const double *d_coef, double *d_out) {
   constexpr int D = Q + 1;
@@ -99,7 +174,7 @@ int main() {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int n_sm = prop.multiProcessorCount;
-  std::vector<double> h(4096);
+  std::vector<double> h(8192);
   for (size_t i = 0; i < h.size(); i++) h[i] = 1e-3 * ((i * 2654435761u) % 1000) - 0.5;
   double *d_coef, *d_out;
   CK(cudaMalloc(&d_coef, h.size() * 8));
@@ -108,6 +183,14 @@ int main() {
   printf("device %s, %d SMs\n", prop.name, n_sm);
   // occupancy sweep of the shipped q=14 shape (255 regs -> 2 CTAs/SM)
   run<14, 2, false, false, 1>("ppt2 regs", 1, n_sm, d_coef, d_out);
+  run_src<14, 2, 1, 1>("ppt2 LDG.256 via L1", 1, n_sm, d_coef, d_out);
+  run_src<14, 2, 1, 1>("ppt2 LDG.256 via L1", 2, n_sm, d_coef, d_out);
+  CK(cudaMemcpyToSymbol(g_coef_const, h.data(), sizeof(double) * 2048));
+  run_src<14, 2, 3, 1>("ppt2 constant operands", 1, n_sm, d_coef, d_out);
+  run_src<14, 2, 3, 1>("ppt2 constant operands", 2, n_sm, d_coef, d_out);
+  run_src<14, 3, 3, 1>("ppt3 constant operands", 2, n_sm, d_coef, d_out);
+  run_src<8, 4, 3, 1>("q8 ppt4 constant operands", 2, n_sm, d_coef, d_out);
+  run_src<8, 4, 1, 1>("q8 ppt4 LDG.256 via L1", 2, n_sm, d_coef, d_out);
   run<14, 2, false, false, 1>("ppt2 regs", 2, n_sm, d_coef, d_out);
   run<14, 2, false, true, 1>("ppt2 regs pair", 1, n_sm, d_coef, d_out);
   run<14, 2, false, true, 1>("ppt2 regs pair", 2, n_sm, d_coef, d_out);
