@@ -594,6 +594,8 @@ def run_b200(args):
     flops = args.steps * (n_local * (n_eval_vel * workloads.flops_per_point_eval(wl.q, 3)
                                      + workloads.flops_per_point_eval(wl.q, 1))
                           + n_exc * workloads.flops_per_point_eval(wl.q, 3))
+    dfma_flops = 2 * (ftm.ncoef(wl.q) - 1)  # executed by the contraction per point and component
+    flops_exec = args.steps * (n_local * (n_eval_vel * 3 + 1) + n_exc * 3) * dfma_flops
     coef_bytes = 8.0 * ftm.ncoef(wl.q) / P
     bytes_alg = args.steps * (n_local * (n_eval_vel * (24 + 24 + 3 * coef_bytes) + (24 + 8 + coef_bytes))
                               + n_exc * (24 + 24 + 3 * coef_bytes))
@@ -608,6 +610,12 @@ def run_b200(args):
         "peak_source": "measured in this run: DFMA-only kernel, best of 5 (MEASURED_PEAKS.json has "
                        "no FP64 entry; nominal 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2)",
         "flops_model": "reference's own: N*(9d + 2*dof*Ncoef), tree_functor.h:389-394",
+        # what the kernel executes: one DFMA per coefficient but the first (T_0 = 1 inside the leaf, so
+        # fma(1, c, 0) is c itself: Ncoef - 1 DFMAs per point and component), i.e. LESS than the model's
+        # 2*Ncoef + closes -- `frac` (model flops over the DFMA peak) can therefore exceed the pipe's own
+        # utilisation, which is `frac_executed_dfma`
+        "frac_executed_dfma": (flops_exec / (ev["ms"] * 1e-3) * 1e-12 / peak_fp64)
+        if (peak_fp64 and ev["ms"] > 0) else None,
         "avg_launch_ms": ev["ms"] / max(1, ev["launches"]), "launches": ev["launches"],
         "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": bytes_alg / max(1, ev["launches"]),

@@ -229,7 +229,8 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
   for (;;) {
     cp_async_wait_all();  // points(n), geom(n) and perm(n+1) have landed
     __syncwarp();
-    double px[PPT][D], py[PPT][D], zc[PPT], z0[PPT];
+    bool inside[PPT];  // a point outside its leaf in any axis evaluates to 0 (all-zero bases: cheb_poly)
+    double px[PPT][D], py[PPT][D], zc[PPT];
     {
       const unsigned n = (unsigned)s_ctl[CT_N];
       // ---- bases of tile n ------------------------------------------------------------
@@ -241,11 +242,11 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
         const double xi = __dadd_rn(__dmul_rn(__dsub_rn(s_x[o], gx), gw), -1.0);
         const double yi = __dadd_rn(__dmul_rn(__dsub_rn(s_x[TP + o], gy), gw), -1.0);
         const double zi = __dadd_rn(__dmul_rn(__dsub_rn(s_x[2 * TP + o], gz), gw), -1.0);
-        cheb_basis<Q>(xi, px[s]);
-        cheb_basis<Q>(yi, py[s]);
+        const bool inx = cheb_basis<Q>(xi, px[s]);
+        const bool iny = cheb_basis<Q>(yi, py[s]);
         const bool inz = fabs(zi) <= 1.0;
         zc[s] = inz ? zi : 0.0;
-        z0[s] = inz ? 1.0 : 0.0;
+        inside[s] = inx && iny && inz;
       }
       __syncwarp();  // every lane has consumed the staging area
       // ---- keep two tiles in flight ----------------------------------------------------
@@ -280,11 +281,12 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
       double u[PPT], tz0[PPT], tz1[PPT];
 #pragma unroll
       for (int s = 0; s < PPT; s++) u[s] = tz0[s] = tz1[s] = 0.0;
-      ZLevel<Q, PPT, false, TB_WT_PAIR != 0, 0, 0>::run(C2, px, py, nullptr, zc, z0, tz0, tz1, u);
+      ZLevel<Q, PPT, false, TB_WT_PAIR != 0, 0, 0>::run(C2, px, py, nullptr, zc, tz0, tz1, u);
       const unsigned n = (unsigned)s_ctl[CT_N];
       const unsigned cnt0 = ring_cnt(n);
 #pragma unroll
       for (int s = 0; s < PPT; s++) {
+        if (!inside[s]) u[s] = 0.0;
         const unsigned o = s * 32 + lane;
         if (o < cnt0) {
           const size_t i = s_perm[(n % 3) * TP + o];
