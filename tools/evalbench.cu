@@ -112,6 +112,88 @@ steady_src_kernel(const double *__restrict__ coef, unsigned stride, double *__re
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// Register-footprint proxies: the real contraction code, but the basis arrays are filled from a few values so
+// that the compiler keeps fewer registers (PXM: px[k] = px[k mod PXM], PYM likewise).  Arithmetic is meaningless;
+// the instruction mix, the dependency chains and the coefficient loads are the real ones.  Answers "what would
+// three or four points per thread reach if the bases needed fewer registers".
+template <int Q, int PPT, int PXM, int PYM, int MINB, bool NOLOAD = false>
+__global__ void __launch_bounds__(kEvalThreads, MINB)
+steady_proxy_kernel(const double *__restrict__ coef, unsigned stride, double *__restrict__ out, int iters) {
+  constexpr int D = Q + 1;
+  extern __shared__ __align__(128) double s_coef[];
+  for (unsigned i = threadIdx.x; i < 2 * stride; i += blockDim.x) s_coef[i] = coef[i];
+  __syncthreads();
+  double bx[PPT][PXM], by[PPT][PYM], zc[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; s++) {
+#pragma unroll
+    for (int k = 0; k < PXM; k++) bx[s][k] = 0.9 - 1.7e-3 * threadIdx.x + 0.011 * s - 0.05 * k;
+#pragma unroll
+    for (int k = 0; k < PYM; k++) by[s][k] = 0.8 - 2.1e-3 * threadIdx.x - 0.007 * s - 0.04 * k;
+    zc[s] = 0.3 - 1e-3 * threadIdx.x;
+  }
+  double acc[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; s++) acc[s] = 0;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    double px[PPT][D], py[PPT][D];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+      bx[s][1 % PXM] += 1e-13;
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        px[s][k] = bx[s][k % PXM];
+        py[s][k] = by[s][k % PYM];
+      }
+    }
+    const double2 *C2 = reinterpret_cast<const double2 *>(s_coef + (it & 1) * stride);
+    double u[PPT], tz0[PPT], tz1[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) u[s] = tz0[s] = tz1[s] = 0.0;
+    if (NOLOAD) {  // coefficients from two registers: the DFMA stream alone
+      CoefReg c{1e-3 * it + 0.25, 0.5 - 1e-3 * it};
+      ZLevel<Q, PPT, false, false, 0, 0>::run(c, px, py, nullptr, zc, tz0, tz1, u);
+    } else {
+      ZLevel<Q, PPT, false, false, 0, 0>::run(C2, px, py, nullptr, zc, tz0, tz1, u);
+    }
+#pragma unroll
+    for (int s = 0; s < PPT; s++) acc[s] += u[s];
+  }
+  double r = 0;
+#pragma unroll
+  for (int s = 0; s < PPT; s++) r += acc[s];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+template <int Q, int PPT, int PXM, int PYM, int MINB, bool NOLOAD = false>
+void run_proxy(const char *name, int ctas_per_sm, int n_sm, const double *d_coef, double *d_out) {
+  constexpr int D = Q + 1;
+  const unsigned ncoef = D * (D + 1) * (D + 2) / 6, stride = ncoef + (ncoef & 1);
+  const size_t smem = 2 * stride * sizeof(double);
+  auto k = steady_proxy_kernel<Q, PPT, PXM, PYM, MINB, NOLOAD>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, k));
+  const int iters = 400, grid = n_sm * ctas_per_sm;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0));
+    k<<<grid, kEvalThreads, smem>>>(d_coef, stride, d_out, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep && ms < best) best = ms;
+  }
+  const double dfma = (double)(ncoef - 1) * PPT * kEvalThreads * (double)grid * iters;
+  printf("%-28s q=%d ppt=%d px regs %d py regs %d regs=%3d local=%zu ctas/sm=%d : %.3f ms  %.2f TFLOP/s (executed DFMA)\n", name, Q,
+         PPT, PXM, PYM, fa.numRegs, (size_t)fa.localSizeBytes, ctas_per_sm, best, 2 * dfma / best * 1e-9);
+}
+
 template <int Q, int PPT, int SRC, int MINB>
 void run_src(const char *name, int ctas_per_sm, int n_sm, const double *d_coef, double *d_out) {
   constexpr int D = Q + 1;
@@ -179,6 +261,19 @@ int main() {
   CK(cudaMemcpy(d_coef, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_out, sizeof(double) * kEvalThreads * n_sm * 8));
   printf("device %s, %d SMs\n", prop.name, n_sm);
+  run_proxy<14, 2, 15, 15, 1>("proxy ppt2 full bases", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 3, 15, 15, 1>("proxy ppt3 full bases", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 3, 8, 15, 1>("proxy ppt3 px/2", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 3, 15, 2, 1>("proxy ppt3 py by 2 regs", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 3, 8, 8, 1>("proxy ppt3 px/2 py/2", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 4, 8, 8, 1>("proxy ppt4 px/2 py/2", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 4, 8, 2, 1>("proxy ppt4 px/2 py 2 regs", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 4, 2, 2, 1>("proxy ppt4 2+2 regs", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 2, 15, 15, 1, true>("proxy ppt2 full, NO LOADS", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 4, 8, 8, 1, true>("proxy ppt4 px/2 py/2, NO LOADS", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 4, 2, 2, 1, true>("proxy ppt4 2+2, NO LOADS", 2, n_sm, d_coef, d_out);
+  run_proxy<14, 4, 2, 2, 1, true>("proxy ppt4 2+2, NO LOADS", 4, n_sm, d_coef, d_out);
+  run_proxy<14, 4, 2, 2, 3, true>("proxy ppt4 2+2, NO LOADS", 3, n_sm, d_coef, d_out);
   // occupancy sweep of the shipped q=14 shape (255 regs -> 2 CTAs/SM)
   run<14, 2, false, false, 1>("ppt2 regs", 1, n_sm, d_coef, d_out);
   run_src<14, 2, 1, 1>("ppt2 LDG.256 via L1", 1, n_sm, d_coef, d_out);

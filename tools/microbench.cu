@@ -46,6 +46,38 @@ __global__ void dfma_kernel(double *out, int iters, double a, double b, long lon
   if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
+// ------------------------------------------- 1b. DFMA with the contraction's operand pattern
+// acc[s] = fma(x[s][k], c[k], acc[s]): a FRESH multiplicand register per instruction, the coefficient register
+// shared by the PPT instructions of one k (operand reuse), the accumulator -- everything in registers, no
+// loads.  dfma_kernel above reads the same two registers (a, b) in every instruction; this one asks the
+// register file for two fresh 64-bit operands per DFMA, as the Chebyshev contraction does.
+template <int PPT, int NX, int NC>
+__global__ void dfma_pattern_kernel(double *out, int iters, double a, long long *cyc) {
+  double x[PPT][NX], c[NC], acc[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; s++) {
+    acc[s] = threadIdx.x * 1e-3 + s;
+#pragma unroll
+    for (int k = 0; k < NX; k++) x[s][k] = 1.0 + 1e-9 * (threadIdx.x + 3 * k + 7 * s) * a;
+  }
+#pragma unroll
+  for (int k = 0; k < NC; k++) c[k] = 1e-9 * (k + 1) * a;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < NX; k++) {
+#pragma unroll
+      for (int s = 0; s < PPT; s++) acc[s] = fma(x[s][k], c[k % NC], acc[s]);
+    }
+  }
+  long long t1 = clock64();
+  double r = 0;
+#pragma unroll
+  for (int s = 0; s < PPT; s++) r += acc[s];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 // ------------------------------------------------------- 2/3. LDS broadcast mix
 // Each iteration: one broadcast load of VEC doubles from shared memory (address is
 // warp-uniform but data dependent on the loop counter so it cannot be hoisted),
@@ -197,6 +229,23 @@ void run_dfma(int threads, int ctas_per_sm) {
          per_sm_clk, cyc / ms * 1e-3);
 }
 
+template <int PPT, int NX, int NC>
+void run_dfma_pattern(int threads, int ctas_per_sm) {
+  const int iters = 4096;
+  Timer t;
+  auto k = dfma_pattern_kernel<PPT, NX, NC>;
+  k<<<n_sm * ctas_per_sm, threads>>>(d_out, 8, 1.0000001, d_cyc);
+  CK(cudaDeviceSynchronize());
+  t.start();
+  k<<<n_sm * ctas_per_sm, threads>>>(d_out, iters, 1.0000001, d_cyc);
+  float ms = t.stop();
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, k));
+  double total = (double)iters * NX * PPT * threads * ctas_per_sm * n_sm;
+  printf("dfma pattern: %d points x %d fresh multiplicands, %d coefficient regs, regs=%d threads=%d ctas/sm=%d warps/smsp=%.1f : %.2f TFLOP/s\n",
+         PPT, NX, NC, fa.numRegs, threads, ctas_per_sm, threads * ctas_per_sm / 128.0, 2 * total / ms * 1e-9);
+}
+
 template <int VEC, int P>
 void run_mix(int threads, int ctas_per_sm) {
   const int iters = 1024;
@@ -274,6 +323,16 @@ int main() {
 
   printf("--- 1. DFMA peak / latency\n");
   run_dfma<8>(1024, 2);
+  printf("--- 1b. DFMA with fresh register operands (the contraction's pattern), no loads\n");
+  run_dfma_pattern<2, 14, 14>(128, 2);
+  run_dfma_pattern<2, 14, 14>(256, 1);
+  run_dfma_pattern<2, 14, 14>(256, 4);
+  run_dfma_pattern<4, 14, 14>(128, 2);
+  run_dfma_pattern<4, 14, 14>(256, 4);
+  run_dfma_pattern<4, 14, 2>(256, 4);
+  run_dfma_pattern<8, 14, 14>(256, 2);
+  run_dfma_pattern<8, 2, 2>(256, 4);
+  printf("--- 1. (continued)\n");
   run_dfma<8>(256, 4);
   run_dfma<4>(256, 4);
   run_dfma<2>(256, 4);
