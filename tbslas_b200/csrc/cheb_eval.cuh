@@ -7,8 +7,8 @@
 // with the RK2 position update of tbslas::IntegrateRK2 (src/semilag/traj.inc:34-42).
 //
 // Design (B200, measured in profiles/r01_microbench_fp64_lds.txt):
-//   * FP64-pipe bound: Ncoef + d(d+1)/2 + d DFMA per point per dof.  DFMA issues every
-//     2 cycles per sub-partition with 8 cycles latency -> >= 4 independent chains.
+//   * FP64-pipe bound: Ncoef - 1 DFMA per point per dof (one per coefficient, see RowPair).  DFMA
+//     issues every 2 cycles per sub-partition with 8 cycles latency -> >= 4 independent chains.
 //   * A warp-broadcast LDS.64 costs 1 SM-cycle, a warp DFMA 0.5: every coefficient read
 //     from shared memory must feed >= 3-4 DFMAs, so each thread owns PPT points and the
 //     T_k(x), T_j(y) of all of them live in registers (loops fully unrolled per degree);
@@ -145,8 +145,8 @@ struct RowPair {
     // T_0 = 1 wherever the point lies inside the leaf (and the caller zeroes the value of a point
     // outside, where every basis value is 0: cheb_poly semantics), so the k = 0 term of a row is the
     // coefficient itself, the j = 0 row of a plane is its row sum, and plane 0 is its own sum: fma(1, c, 0)
-    // == c exactly, i.e. the same bits for Ncoef - (rows + planes + 1) fewer DFMAs (815 -> 679 per point and
-    // component at q = 14, 219 -> 164 at q = 8).
+    // == c exactly, i.e. the same bits for rows + planes + 1 fewer DFMAs: Ncoef - 1 per point and component
+    // (815 -> 679 at q = 14, 219 -> 164 at q = 8).
     double w0[PPT], w1[PPT];
 #pragma unroll
     for (int k = 0; k < N0; k++) {

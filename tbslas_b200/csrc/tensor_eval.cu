@@ -10,7 +10,7 @@
 //     A[i][j][px] = sum_k C[i][j][k] T_k(xi_px)            (120 rows x 15, <= 15 terms)
 //     B[i][py][px] = sum_j A[i][j][px] T_j(eta_py)          (15 x 225, <= 15 terms)
 //     u[pz][py][px] = sum_i B[i][py][px] T_i(zeta_pz)       (3375, 15 terms)
-// = 88 k FMA per leaf and component at q = 14 against 3375 x 815 = 2.75 M for point-by-point
+// = 88 k FMA per leaf and component at q = 14 against 3375 x 679 = 2.29 M for point-by-point
 // evaluation (tree_functor.h:27-84): the same polynomial at the same points, summed in another
 // order (differences ~1e-15 of the field scale).  The coordinates and bases are formed exactly
 // as the generic kernels form them (same expressions, same rounding).
