@@ -792,7 +792,7 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
     ctx->opt.locate_no_boxes = flag("TBSLAS_LOCATE_NO_BOXES", false);
     ctx->opt.tensor_generic = flag("TBSLAS_TENSOR_GENERIC", false);
     if (const char *e = getenv("TBSLAS_TENSOR_DMMA")) ctx->opt.tensor_dmma = atoi(e);
-    if (const char *e = getenv("TBSLAS_TENSOR_CTAS")) ctx->opt.tensor_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 600;
+    if (const char *e = getenv("TBSLAS_TENSOR_CTAS")) ctx->opt.tensor_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 0;
     if (const char *e = getenv("TBSLAS_EVAL_VARIANT")) ctx->opt.eval_variant = atoi(e);
     if (const char *e = getenv("TBSLAS_EXCHANGE")) ctx->opt.peer_exchange = strcmp(e, "nccl") != 0;
     if (const char *e = getenv("TBSLAS_MAILBOX_POINTS")) ctx->opt.mailbox_points = (size_t)strtoull(e, nullptr, 10);

@@ -848,11 +848,267 @@ static int launch_tensor_dmma2(tbslas_ctx *ctx, const TensorParams &p, const Ten
   auto k = tensor_grid_dmma2_kernel<D>;
   TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  const size_t cap = (size_t)ctx->n_sm * (size_t)ctx->opt.tensor_ctas_per_sm;  // persistent: 3 resident CTAs per SM
+  const size_t cap = (size_t)ctx->n_sm * (size_t)(ctx->opt.tensor_ctas_per_sm > 0 ? ctx->opt.tensor_ctas_per_sm : 600);  // one CTA per leaf measured best
   const size_t want = n_leaf < cap ? n_leaf : cap;
   k<<<(unsigned)want, kTensorThreads, smem, ctx->stream>>>(p, tt);
   TB_CUDA(ctx, cudaGetLastError());
   return TBSLAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Third DMMA kernel (q <= 14): the same passes, but pass 3 runs ONCE for the three velocity components, with
+// the component as the fastest index of its column dimension,
+//     U[pz][(py, px, l)] = sum_i Tz[i][pz] B[i][(py, px, l)],
+// so that a warp's 8 x 8 output tile is, for every pz, 64 contiguous bytes of the AoS position array and the
+// three components of a point are written together -- kernel 2 fills every 32-byte sector 8 bytes at a time in
+// three passes microseconds apart (18.3 GB written + 5.0 GB of read-modify-write reads for 13.2 GB).  The price
+// is the B array of all three components resident in shared memory ([D][3 D^2] doubles, 81.6 KB at q = 14), i.e.
+// two CTAs per SM instead of three; the coefficient block is staged one component at a time to make room.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kTensorThreads, 2)
+tensor_grid_dmma3_kernel(const TensorParams p, const TensorTables tb_) {
+  constexpr int P2 = D * D, P = P2 * D, NROW = D * (D + 1) / 2, MT1 = (NROW + 7) / 8, KS = (D + 3) / 4;
+  constexpr int NC = 3 * P2, NB = (NC + 7) & ~7;  // columns of pass 3 (py, px, l), padded to whole tiles
+  constexpr int XG = (3 * P2 + kTensorThreads - 1) / kTensorThreads;
+  static_assert(D <= 15, "the B array of three components must fit two CTAs per SM");
+  extern __shared__ __align__(16) double sm[];
+  double *sT = sm;                    // [3][16][16]  T_deg(point) per axis, degree major, zero padded
+  double *sC = sT + 3 * 256;          // [ncoef_pad]  one component at a time (bulk-TMA destination)
+  double *sA1 = sC + p.ncoef_pad;     // [MT1*8][16]
+  double *sB = sA1 + MT1 * 8 * 16;    // [D][NB]
+  __shared__ double sX[3 * 16];
+  __shared__ double sNode[16];
+  __shared__ uint32_t sRow[MT1 * 8];  // row (i,j): first coefficient | length << 16
+  __shared__ uint32_t sCol[NB];       // column (py, px, l): px | py << 8 | index of its base coordinate in sX << 16 (0xff: z)
+  __shared__ unsigned s_ok[2][4];
+  __shared__ unsigned s_exc[2][2];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int e = t; e < 3 * 256; e += kTensorThreads) sT[e] = 0.0;
+  for (int e = NC + t; e < D * NB; e += kTensorThreads)  // the padding columns of every row stay zero
+    if (e % NB >= NC) sB[e] = 0.0;
+  if (t < 16) sNode[t] = t < D ? tb_.node[t] : 0.0;
+  if (t < MT1 * 8) sRow[t] = t < NROW ? ((uint32_t)tb_.row_off[t] | ((uint32_t)tb_.row_len[t] << 16)) : 0u;
+  for (int c = t; c < NB; c += kTensorThreads) {
+    const int pt = c / 3, l = c - 3 * pt, py = pt / D, px = pt - py * D;
+    sCol[c] = c < NC ? ((uint32_t)px | ((uint32_t)py << 8) | ((uint32_t)(l == 0 ? px : (l == 1 ? 16 + py : 0xff)) << 16))
+                     : 0xffffffffu;
+  }
+  if (t < 8) (&s_ok[0][0])[t] = 0u;
+  if (t < 4) (&s_exc[0][0])[t] = 0u;
+  if (t == 0) mbar_init(&s_bar, 1);
+  int xsel[XG];
+#pragma unroll
+  for (int m = 0; m < XG; m++) {
+    const int r = t + m * kTensorThreads;
+    const int pt = r / 3, a = r - 3 * pt, py = pt / D, px = pt - py * D;
+    xsel[m] = r >= 3 * P2 ? -2 : (a == 0 ? px : (a == 1 ? 16 + py : -1));
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  bool prefetched = false;  // CTA-uniform: component 0 of this leaf's block was requested during the previous leaf
+  int par = 0;
+  for (size_t leaf = blockIdx.x; leaf < p.n_leaf; leaf += gridDim.x, par ^= 1) {
+    const int j = p.map[leaf];
+    const size_t gp0 = leaf * (size_t)P;
+    const double4 gc = p.ggeom[leaf];
+    const double glen = 1.0 / (double)(1u << p.gdepth[leaf]);
+    __syncthreads();  // the previous leaf's passes are done with sT, sX, sB
+    if (t < 3 * D) {
+      const int a = t / D, i = t - a * D;
+      const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z);
+      const double x = __dadd_rn(c, __dmul_rn(glen, sNode[i]));  // gridpts.cu
+      sX[a * 16 + i] = x;
+      if (j >= 0) {
+        const double4 gv = vel_geom(p, j);
+        const uint4 vb = vel_box(p, j);
+        const double vc = a == 0 ? gv.x : (a == 1 ? gv.y : gv.z);
+        const unsigned vba = a == 0 ? vb.x : (a == 1 ? vb.y : vb.z);
+        const double xi = __dadd_rn(__dmul_rn(__dsub_rn(x, vc), gv.w), -1.0);  // cheb_eval.cuh
+        const bool in = fabs(xi) <= 1.0;
+        const double xc = in ? xi : 0.0, x2 = 2.0 * xc;
+        double t0 = in ? 1.0 : 0.0, t1 = xc;
+        double *T = sT + a * 256;
+        T[swz(0, i)] = t0;
+        if (D > 1) T[swz(1, i)] = t1;
+#pragma unroll
+        for (int k = 2; k < D; k++) {
+          const double t2 = __dsub_rn(__dmul_rn(x2, t1), t0);
+          T[swz(k, i)] = t2;
+          t0 = t1;
+          t1 = t2;
+        }
+        const double xs = x * 32768.0;
+        int jx = __double2int_rd(xs);
+        if (!p.periodic && xs == 32768.0) jx = 32767;
+        if ((unsigned)jx < 32768u && ((((unsigned)jx ^ vba) >> vb.w) == 0u)) atomicOr(&s_ok[par][a], 1u << i);
+      }
+    }
+    __syncthreads();
+    const unsigned okx = s_ok[par][0], oky = s_ok[par][1], okz = s_ok[par][2];
+    const unsigned n_reg = (unsigned)(__popc(okx) * __popc(oky) * __popc(okz));
+    const bool passes = j >= 0 && n_reg;  // CTA-uniform
+    auto fetch_comp = [&](int jv, int l) {  // one thread: component l of velocity leaf jv's block -> sC
+      fence_proxy_async_cta();
+      const uint32_t bytes = p.ncoef_pad * 8u;
+      mbar_expect_tx(&s_bar, bytes);
+      tma_bulk_g2s(sC, vel_coeff(p, jv) + (size_t)l * p.ncoef_pad, bytes, &s_bar);
+    };
+    if (passes && !prefetched && t == 0) fetch_comp(j, 0);
+    if (!passes && prefetched) {  // requested for nothing (every point of the leaf is an exception): keep the phases in step
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+    }
+    prefetched = false;
+    if (t == 0 && n_reg < (unsigned)P) s_exc[par][0] = atomicAdd(p.exc_count, (unsigned)P - n_reg);
+    if (t < 3) s_ok[par ^ 1][t] = 0u;
+    if (t == 0) s_exc[par ^ 1][1] = 0u;
+    if (p.xgen) {  // arrival points of this leaf: a table expansion, fully coalesced
+      double xv[XG];
+#pragma unroll
+      for (int m = 0; m < XG; m++) xv[m] = xsel[m] >= 0 ? sX[xsel[m]] : 0.0;
+      double *o = p.xgen + 3 * gp0 + t;
+#pragma unroll 5
+      for (int pz = 0; pz < D; pz++) {
+        const double zq = sX[32 + pz];
+#pragma unroll
+        for (int m = 0; m < XG; m++)
+          if (xsel[m] != -2) TB_TENSOR_XSTORE(o + pz * 3 * P2 + m * kTensorThreads, xsel[m] == -1 ? zq : xv[m]);
+      }
+    }
+    if (passes) {
+      for (int l = 0; l < 3; l++) {
+        mbar_wait(&s_bar, phase);  // component l has landed
+        phase ^= 1u;
+        // ---- pass 1: A1[r][px] = sum_k Cpad[r][k] Tx[k][px]
+        {
+          const int nt = warp & 1;
+          const double *pb = sT + lc * 16 + ((nt * 8 + lr) ^ (lc << 2));
+          double b[KS];
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) b[ks] = pb[ks * 64];
+          for (int mt = warp >> 1; mt < MT1; mt += kTensorThreads / 64) {
+            const int r = mt * 8 + lr;
+            const uint32_t rw = sRow[r];
+            const int rlen = (int)(rw >> 16);
+            const double *pa = sC + (rw & 0xffffu) + lc;
+            const int nks = (tb_.tile_k[mt] + 3) >> 2;
+            double a[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) a[ks] = ks * 4 + lc < rlen ? pa[ks * 4] : 0.0;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+              if (ks < nks) dmma884(c0, c1, a[ks], b[ks]);
+            *reinterpret_cast<double2 *>(sA1 + swz(r, nt * 8 + 2 * lc)) = make_double2(c0, c1);
+          }
+        }
+        __syncthreads();
+        if (l < 2) {  // sC is free: the next component lands under pass 2 ...
+          if (t == 0) fetch_comp(j, l + 1);
+        } else {      // ... and after the last one, component 0 of the next leaf under passes 2 and 3
+          const size_t next = leaf + gridDim.x;
+          if (next < p.n_leaf) {
+            const int jn = p.map[next];
+            if (jn >= 0) {
+              if (t == 0) fetch_comp(jn, 0);
+              prefetched = true;
+            }
+          }
+        }
+        // ---- pass 2: B[i][(py, px, l)] = sum_j Ty[j][py] A1[(i,j)][px]
+        {
+          const int mt = warp & 1, nt = (warp >> 1) & 1;
+          const double *pa = sT + 256 + lc * 16 + ((mt * 8 + lr) ^ (lc << 2));
+          double a[KS];
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) a[ks] = pa[ks * 64];
+          const int py = mt * 8 + lr, px = nt * 8 + 2 * lc;
+          for (int i = warp >> 2; i < D; i += kTensorThreads / 128) {
+            const int nj = D - i, rb = tb_.row_first[i] + lc;
+            const double *pbb = sA1 + rb * 16 + ((nt * 8 + lr) ^ ((rb & 3) << 2));
+            double b[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) b[ks] = ks * 4 + lc < nj ? pbb[ks * 64] : 0.0;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+              if (ks * 4 < nj) dmma884(c0, c1, a[ks], b[ks]);
+            if (py < D) {
+              double *o = sB + i * NB + 3 * (py * D + px) + l;
+              if (px < D) o[0] = c0;
+              if (px + 1 < D) o[3] = c1;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // ---- pass 3, all components: U[pz][c] = sum_i Tz[i][pz] B[i][c];  x' = x + alpha U on regular points
+      double az[2][KS];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) az[mt][ks] = sT[512 + swz(ks * 4 + lc, mt * 8 + lr)];
+      double *const ob = p.out + 3 * gp0;
+      for (int nt = warp; nt < NB / 8; nt += kTensorThreads / 32) {
+        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const double *pb = sB + lc * NB + nt * 8 + lr;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+          const double b = ks * 4 + lc < D ? pb[ks * 4 * NB] : 0.0;
+          dmma884(c[0][0], c[0][1], az[0][ks], b);
+          dmma884(c[1][0], c[1][1], az[1][ks], b);
+        }
+        const int col0 = nt * 8 + 2 * lc;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t ci = sCol[col0 + h];
+          if (ci == 0xffffffffu) continue;
+          const int px = (int)(ci & 0xffu), py = (int)((ci >> 8) & 0xffu), sel = (int)(ci >> 16);
+          if (!((okx >> px) & (oky >> py) & 1u)) continue;
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) {
+            const int pz = mt * 8 + lr;
+            if (pz >= D || !((okz >> pz) & 1u)) continue;
+            const double x0 = sX[sel == 0xff ? 32 + pz : sel];
+            ob[pz * NC + col0 + h] = __dadd_rn(x0, __dmul_rn(p.alpha, c[mt][h]));  // traj.inc:36
+          }
+        }
+      }
+    }
+    if (n_reg < (unsigned)P) {  // list the exceptions of this leaf (CTA-uniform condition)
+      __syncthreads();
+      const unsigned base = s_exc[par][0];
+      for (int e = t; e < P; e += kTensorThreads) {
+        const int pz = e / P2, rem = e - pz * P2, py = rem / D, px = rem - py * D;
+        if (j >= 0 && (((okx >> px) & (oky >> py) & (okz >> pz)) & 1u)) continue;
+        const unsigned k = atomicAdd(&s_exc[par][1], 1u);
+        p.exc_idx[base + k] = (uint32_t)(gp0 + e);
+      }
+    }
+  }
+}
+
+template <int D>
+static int launch_tensor_dmma3(tbslas_ctx *ctx, const TensorParams &p, const TensorTables &tt, size_t n_leaf) {
+  if constexpr (D > 15) {
+    return launch_tensor_dmma2<D>(ctx, p, tt, n_leaf);
+  } else {
+    constexpr int NROW = D * (D + 1) / 2, MT1 = (NROW + 7) / 8, NB = (3 * D * D + 7) & ~7;
+    const size_t smem = sizeof(double) * ((size_t)3 * 256 + p.ncoef_pad + (size_t)MT1 * 8 * 16 + (size_t)D * NB);
+    auto k = tensor_grid_dmma3_kernel<D>;
+    TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    // 2 resident CTAs per SM; flat between 2 and 16 CTAs per SM (4.80-4.83 ms on C2), 5.2 at 32, 5.4 per leaf
+    const int per_sm = ctx->opt.tensor_ctas_per_sm > 0 ? ctx->opt.tensor_ctas_per_sm : 8;
+    const size_t cap = (size_t)ctx->n_sm * (size_t)per_sm;
+    const size_t want = n_leaf < cap ? n_leaf : cap;
+    k<<<(unsigned)want, kTensorThreads, smem, ctx->stream>>>(p, tt);
+    TB_CUDA(ctx, cudaGetLastError());
+    return TBSLAS_OK;
+  }
 }
 
 __global__ void publish_count_kernel(const unsigned *__restrict__ src, unsigned *host_word) {
@@ -987,13 +1243,14 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
     p.exc_count = exc_count;
     p.exc_idx = (uint32_t *)exc_idx;
     const bool force_generic = ctx->opt.tensor_generic;
-    const int dmma_mode = ctx->opt.tensor_dmma;  // 0: scalar kernels, 1: first DMMA kernel, 2: the default
+    const int dmma_mode = ctx->opt.tensor_dmma;  // 0: scalar kernels, 1 / 2: earlier DMMA kernels, 3: the default (2 for q = 15)
     bool launched = false;
     if (!force_generic && dmma_mode) {
       switch (d) {
 #define TB_CASE(DD) \
   case DD:          \
-    TB_TRY(dmma_mode == 1 ? launch_tensor_dmma<DD>(ctx, p, tt, n_leaf) : launch_tensor_dmma2<DD>(ctx, p, tt, n_leaf)); \
+    TB_TRY(dmma_mode == 1 ? launch_tensor_dmma<DD>(ctx, p, tt, n_leaf)                                      \
+                          : (dmma_mode == 3 ? launch_tensor_dmma3<DD>(ctx, p, tt, n_leaf) : launch_tensor_dmma2<DD>(ctx, p, tt, n_leaf))); \
     launched = true; \
     break;
         TB_CASE(9) TB_CASE(10) TB_CASE(11) TB_CASE(12) TB_CASE(13) TB_CASE(14) TB_CASE(15) TB_CASE(16)
