@@ -2,5 +2,6 @@ python -m pytest tests -m gpu -x -q > gpurun_out/r2f_pytest.log 2>&1; echo "pyte
 python bench.py > gpurun_out/r2f_c2.json 2> gpurun_out/r2f_c2.err
 python bench.py --impl reference > gpurun_out/r2f_ref.json 2> gpurun_out/r2f_ref.err
 for w in c1 c3 c4 c5; do python bench.py --workload $w --no-cpu > gpurun_out/r2f_$w.json 2> gpurun_out/r2f_$w.err; done
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-parity > gpurun_out/r2f_ncu_launch.log 2>&1
-tail -n 2 gpurun_out/r2f_pytest.log
+bash tools/launchlist.sh
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2f_smoke.log 2>&1
+tail -n 2 gpurun_out/r2f_pytest.log gpurun_out/r2f_smoke.log
