@@ -159,11 +159,11 @@ struct tbslas_ctx {
   int exchange_mode = 1;  // 1: peer-memory mailboxes where available, 0: NCCL all-to-all-v
   // A/B switches of the kernels, read from the environment ONCE, at tbslas_b200_init, into the context
   // (no process-global state in the hot functions): TBSLAS_EXCHANGE_FIRST=0, TBSLAS_LOCATE_NO_BOXES=1,
-  // TBSLAS_TENSOR_GENERIC=1, TBSLAS_TENSOR_DMMA=0|1|2, TBSLAS_TENSOR_CTAS=<n per SM>, TBSLAS_EVAL_VARIANT=1|2, TBSLAS_EXCHANGE=nccl,
+  // TBSLAS_TENSOR_GENERIC=1, TBSLAS_TENSOR_DMMA=0|2, TBSLAS_TENSOR_CTAS=<n per SM>, TBSLAS_EVAL_VARIANT=1|2, TBSLAS_EXCHANGE=nccl,
   // TBSLAS_MAILBOX_POINTS=<n>
   struct Options {
     bool exchange_first = true, locate_no_boxes = false, tensor_generic = false;
-    int tensor_dmma = 3;          // 0: scalar tensor-grid kernels, 1 / 2: earlier DMMA kernels, 3: the default
+    int tensor_dmma = 3;          // 0: scalar tensor-grid kernels, 2: second DMMA kernel, 3: third (the default)
     int tensor_ctas_per_sm = 0;   // grid cap of the DMMA kernels per SM (0: the kernel's own measured best)
     bool peer_exchange = true;
     int eval_variant = 0;

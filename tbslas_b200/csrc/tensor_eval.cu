@@ -448,166 +448,10 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // 4*(row mod 4) spreads them over the banks without padding.
 __device__ __forceinline__ int swz(int row, int col) { return row * 16 + (col ^ ((row & 3) << 2)); }
 
-template <int D>
-__global__ void __launch_bounds__(kTensorThreads, 3)
-tensor_grid_dmma_kernel(const TensorParams p, const TensorTables tb_) {
-  constexpr int P2 = D * D, P = P2 * D, NROW = D * (D + 1) / 2, MT1 = (NROW + 7) / 8, KS = (D + 3) / 4;
-  static_assert(D <= 16, "one 16-wide tile per axis");
-  extern __shared__ __align__(16) double sm[];
-  double *sT = sm;                    // [3][16][16]  T_deg(point) per axis, degree major, zero padded
-  double *sC3 = sT + 3 * 256;         // [3][ncoef_pad]
-  double *sA1 = sC3 + p.vstride;      // [MT1*8][16]
-  double *sB2 = sA1 + MT1 * 8 * 16;   // [16][16][16]  (plane, py, px)
-  __shared__ unsigned s_ok[3];
-  __shared__ unsigned s_exc_base, s_exc_n;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int lr = lane >> 2, lc = lane & 3;  // fragment row / column index of this lane
-  for (int e = t; e < 16 * 256; e += kTensorThreads) sB2[e] = 0.0;  // planes >= D stay zero
-  for (size_t leaf = blockIdx.x; leaf < p.n_leaf; leaf += gridDim.x) {
-    const int j = p.map[leaf];
-    const size_t gp0 = leaf * (size_t)P;
-    __syncthreads();
-    const double4 gc = p.ggeom[leaf];
-    const double glen = 1.0 / (double)(1u << p.gdepth[leaf]);
-    if (p.xgen) {  // arrival points of this leaf, formed exactly as gridpts.cu forms them
-      double *o = p.xgen + 3 * gp0;
-      for (int e = t; e < 3 * P; e += kTensorThreads) {
-        const int pt = e / 3, a = e - 3 * pt;
-        const int pz = pt / P2, rem = pt - pz * P2, py = rem / D, px = rem - py * D;
-        const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z);
-        o[e] = __dadd_rn(c, __dmul_rn(glen, tb_.node[a == 0 ? px : (a == 1 ? py : pz)]));
-      }
-    }
-    if (t < 3) s_ok[t] = 0u;
-    if (t == 0) s_exc_n = 0u;
-    for (int e = t; e < 3 * 256; e += kTensorThreads) sT[e] = 0.0;
-    if (j >= 0) {
-      const double *C = vel_coeff(p, j);
-      for (int e = t; e < (int)p.vstride; e += kTensorThreads) sC3[e] = C[e];
-    }
-    __syncthreads();
-    if (j >= 0 && t < 3 * D) {
-      const int a = t / D, i = t - a * D;
-      const double4 gv = vel_geom(p, j);
-      const uint4 vb = vel_box(p, j);
-      const double c = a == 0 ? gc.x : (a == 1 ? gc.y : gc.z), vc = a == 0 ? gv.x : (a == 1 ? gv.y : gv.z);
-      const unsigned vba = a == 0 ? vb.x : (a == 1 ? vb.y : vb.z);
-      const double x = __dadd_rn(c, __dmul_rn(glen, tb_.node[i]));            // gridpts.cu
-      const double xi = __dadd_rn(__dmul_rn(__dsub_rn(x, vc), gv.w), -1.0);  // cheb_eval.cuh
-      const bool in = fabs(xi) <= 1.0;
-      const double xc = in ? xi : 0.0, x2 = 2.0 * xc;
-      double t0 = in ? 1.0 : 0.0, t1 = xc;
-      double *T = sT + a * 256;  // [degree][point], swizzled
-      T[swz(0, i)] = t0;
-      if (D > 1) T[swz(1, i)] = t1;
-#pragma unroll
-      for (int k = 2; k < D; k++) {
-        const double t2 = __dsub_rn(__dmul_rn(x2, t1), t0);
-        T[swz(k, i)] = t2;
-        t0 = t1;
-        t1 = t2;
-      }
-      const double xs = x * 32768.0;
-      int jx = __double2int_rd(xs);
-      if (!p.periodic && xs == 32768.0) jx = 32767;
-      if ((unsigned)jx < 32768u && ((((unsigned)jx ^ vba) >> vb.w) == 0u)) atomicOr(&s_ok[a], 1u << i);
-    }
-    __syncthreads();
-    const unsigned okx = s_ok[0], oky = s_ok[1], okz = s_ok[2];
-    const unsigned n_reg = (unsigned)(__popc(okx) * __popc(oky) * __popc(okz));
-    if (t == 0 && n_reg < (unsigned)P) s_exc_base = atomicAdd(p.exc_count, (unsigned)P - n_reg);
-    if (j >= 0 && n_reg) {
-      // Tz fragments of pass 3 (the same for every column tile and component)
-      double az[2][KS];
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-        for (int ks = 0; ks < KS; ks++) az[mt][ks] = sT[512 + swz(ks * 4 + lc, mt * 8 + lr)];
-      for (int l = 0; l < 3; l++) {
-        const double *C = sC3 + l * p.ncoef_pad;
-        // ---- pass 1: A1[r][px] = sum_k Cpad[r][k] Tx[k][px]
-        for (int job = warp; job < MT1 * 2; job += kTensorThreads / 32) {
-          const int mt = job >> 1, nt = job & 1, r = mt * 8 + lr;
-          const int roff = r < NROW ? tb_.row_off[r] : 0, rlen = r < NROW ? tb_.row_len[r] : 0;
-          const int nks = (tb_.tile_k[mt] + 3) >> 2;
-          double c0 = 0.0, c1 = 0.0;
-          for (int ks = 0; ks < nks; ks++) {
-            const int k = ks * 4 + lc;
-            const double a = k < rlen ? C[roff + k] : 0.0;
-            dmma884(c0, c1, a, sT[swz(k, nt * 8 + lr)]);
-          }
-          *reinterpret_cast<double2 *>(sA1 + swz(r, nt * 8 + 2 * lc)) = make_double2(c0, c1);
-        }
-        __syncthreads();
-        // ---- pass 2: B2[i][py][px] = sum_j Ty[j][py] A1[(i,j)][px]
-        for (int job = warp; job < D * 4; job += kTensorThreads / 32) {
-          const int i = job >> 2, mt = (job >> 1) & 1, nt = job & 1, nj = D - i, rf = tb_.row_first[i];
-          double c0 = 0.0, c1 = 0.0;
-          for (int ks = 0; ks * 4 < nj; ks++) {
-            const int jj = ks * 4 + lc;
-            const double b = jj < nj ? sA1[swz(rf + jj, nt * 8 + lr)] : 0.0;
-            dmma884(c0, c1, sT[256 + swz(jj, mt * 8 + lr)], b);
-          }
-          *reinterpret_cast<double2 *>(sB2 + i * 256 + (mt * 8 + lr) * 16 + ((nt * 8 + 2 * lc) ^ ((i & 3) << 2))) = make_double2(c0, c1);
-        }
-        __syncthreads();
-        // ---- pass 3: U[pz][(py,px)] = sum_i Tz[i][pz] B2[i][(py,px)];  x' = x + alpha U on regular points
-        for (int nt = warp; nt < 2 * D; nt += kTensorThreads / 32) {
-          double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-          for (int ks = 0; ks < KS; ks++) {
-            const double b = sB2[(ks * 4 + lc) * 256 + ((nt * 8 + lr) ^ (lc << 2))];
-            dmma884(c[0][0], c[0][1], az[0][ks], b);
-            dmma884(c[1][0], c[1][1], az[1][ks], b);
-          }
-          const int py = nt >> 1, px0 = (nt & 1) * 8 + 2 * lc;
-          const double yq = __dadd_rn(gc.y, __dmul_rn(glen, tb_.node[py]));
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++) {
-            const int pz = mt * 8 + lr;
-            if (pz >= D || !((oky >> py) & (okz >> pz) & 1u)) continue;
-            const double zq = __dadd_rn(gc.z, __dmul_rn(glen, tb_.node[pz]));
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const int px = px0 + h;
-              if (px >= D || !((okx >> px) & 1u)) continue;
-              const double x0 = l == 0 ? __dadd_rn(gc.x, __dmul_rn(glen, tb_.node[px])) : (l == 1 ? yq : zq);
-              p.out[3 * (gp0 + (size_t)pz * P2 + py * D + px) + l] = __dadd_rn(x0, __dmul_rn(p.alpha, c[mt][h]));  // traj.inc:36
-            }
-          }
-        }
-        // (pass 1 of the next component only writes sA1; its barrier orders pass 2 after this pass 3)
-      }
-    }
-    if (n_reg < (unsigned)P) {  // list the exceptions of this leaf (CTA-uniform condition)
-      __syncthreads();
-      for (int e = t; e < P; e += kTensorThreads) {
-        const int pz = e / P2, rem = e - pz * P2, py = rem / D, px = rem - py * D;
-        if (j >= 0 && (((okx >> px) & (oky >> py) & (okz >> pz)) & 1u)) continue;
-        const unsigned k = atomicAdd(&s_exc_n, 1u);
-        p.exc_idx[s_exc_base + k] = (uint32_t)(gp0 + e);
-      }
-    }
-  }
-}
-
-template <int D>
-static int launch_tensor_dmma(tbslas_ctx *ctx, const TensorParams &p, const TensorTables &tt, size_t n_leaf) {
-  constexpr int NROW = D * (D + 1) / 2, MT1 = (NROW + 7) / 8;
-  const size_t smem = sizeof(double) * ((size_t)3 * 256 + p.vstride + (size_t)MT1 * 8 * 16 + 16 * 256);
-  auto k = tensor_grid_dmma_kernel<D>;
-  TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  const size_t want = n_leaf < (size_t)ctx->n_sm * 12 ? n_leaf : (size_t)ctx->n_sm * 12;
-  k<<<(unsigned)want, kTensorThreads, smem, ctx->stream>>>(p, tt);
-  TB_CUDA(ctx, cudaGetLastError());
-  return TBSLAS_OK;
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// Second DMMA kernel (round 2, the default): the same three GEMM passes and the same values, with the
-// per-leaf work AROUND the GEMMs taken off the critical path.  ncu of the first version showed 4 % FP64
+// Second DMMA kernel (round 2; runs q = 15, and q <= 14 as an A/B switch): the three GEMM passes with the
+// per-leaf work AROUND the GEMMs taken off the critical path.  ncu of the first version (round 2's first
+// session; removed) showed 4 % FP64
 // and 46 % issue utilisation with 82 k SM-clocks per three leaves: the time went into (a) the arrival-point
 // loop (four integer divisions and a lane-divergent constant-bank load per element), (b) lane-divergent
 // constant-bank loads of the row tables and nodes inside the passes (an LDC with different indices in a
@@ -1243,14 +1087,13 @@ int launch_tensor_grid_eval(tbslas_ctx *ctx, tbslas_tree *vel, const tbslas_tree
     p.exc_count = exc_count;
     p.exc_idx = (uint32_t *)exc_idx;
     const bool force_generic = ctx->opt.tensor_generic;
-    const int dmma_mode = ctx->opt.tensor_dmma;  // 0: scalar kernels, 1 / 2: earlier DMMA kernels, 3: the default (2 for q = 15)
+    const int dmma_mode = ctx->opt.tensor_dmma;  // 0: scalar kernels, 2: the second DMMA kernel, 3: the default (2 for q = 15)
     bool launched = false;
     if (!force_generic && dmma_mode) {
       switch (d) {
 #define TB_CASE(DD) \
   case DD:          \
-    TB_TRY(dmma_mode == 1 ? launch_tensor_dmma<DD>(ctx, p, tt, n_leaf)                                      \
-                          : (dmma_mode == 3 ? launch_tensor_dmma3<DD>(ctx, p, tt, n_leaf) : launch_tensor_dmma2<DD>(ctx, p, tt, n_leaf))); \
+    TB_TRY(dmma_mode >= 3 ? launch_tensor_dmma3<DD>(ctx, p, tt, n_leaf) : launch_tensor_dmma2<DD>(ctx, p, tt, n_leaf)); \
     launched = true; \
     break;
         TB_CASE(9) TB_CASE(10) TB_CASE(11) TB_CASE(12) TB_CASE(13) TB_CASE(14) TB_CASE(15) TB_CASE(16)

@@ -202,6 +202,39 @@ def test_gpu_partial_tree_null_leaf(ctx, port):
     assert rel_err(v, vo) < RTOL
 
 
+@pytest.mark.parametrize("q", [8, 14])
+def test_gpu_points_outside_their_leaf_evaluate_to_zero(ctx, port, q):
+    """cheb_poly makes every basis value 0 for a coordinate outside [-1, 1], so a point that
+    the assignment rule puts into a leaf whose box does not contain it -- every point behind the last leaf
+    of a rank's shard -- evaluates to exactly 0, in one, two or three axes alike.  The evaluation kernels
+    never read T_0 (inside the leaf it is 1) and zero such points with a select: checked here on
+    the unrolled kernels the benchmarks run (q = 8 and 14, three components), through the plain store and
+    through the fused RK2 update (x + alpha * 0 must be x itself)."""
+    api = _api()
+    coord, dd = ftm.uniform_leaves(2)
+    ft = ftm.random_tree(coord, dd, q, 3, seed=31 + q).shard(9, 41)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    pts = np.random.default_rng(6).uniform(0, 1, size=(20000, 3))
+    vo, lo, _ = port.eval_tree(h, 3, pts, 0)
+    v, leaf = f.eval_with_leaf(pts.copy(), 0)
+    assert np.array_equal(leaf, lo)
+    size = np.power(0.5, dd[9:41].astype(np.float64))
+    inside = np.zeros(len(pts), bool)
+    ok = lo >= 0
+    rel = (pts[ok] - ft.coord[lo[ok]]) / size[lo[ok], None]
+    inside[ok] = ((rel >= 0) & (rel <= 1)).all(axis=1)
+    outside = ok & ~inside
+    assert outside.sum() > 1000 and inside.sum() > 1000
+    assert np.all(v[outside] == 0.0) and np.all(vo[outside] == 0.0)
+    assert rel_err(v, vo) < RTOL
+    xo = port.traj_rk2(h, pts, 0.02, 0.0, 1, 0)
+    x = api.ComputeTrajRK2(f, pts, 0.02, 0.0, 1, 0)
+    assert np.abs(x - xo).max() < RTOL
+    still = outside & (np.abs(xo - pts).max(axis=1) == 0.0)  # never entered the shard: did not move at all
+    assert still.sum() > 100 and np.array_equal(x[still], pts[still])
+
+
 @pytest.mark.parametrize("bc", [0, 1])
 def test_gpu_locate_faces_corners_and_leaf_major_streams(ctx, port, bc):
     """The box fast path of the locate kernel: points exactly on leaf faces, edges
