@@ -443,7 +443,8 @@ static int traj_rk2_dev(const tbslas_field *f1, const tbslas_field *f2, int bc, 
           // in its epilogue (one tree, persistent kernel), the arrival points are never written.
           const tbslas_field *fs2 = f2 ? f2 : f1;
           const bool virt = gen_points && ctx->virtual_x && tensor_grid_supports_virtual_x(one) &&
-                            field_is_single(ctx, fs2) && eval_supports_grid_base(fs2->tree[0]);
+                            field_is_single(ctx, fs2) && eval_supports_grid_base(fs2->tree[0]) &&
+                            fs2->tree[0]->q == grid->q;  // (the epilogue decodes node indices at the kernel's degree)
           const int rc = launch_tensor_grid_eval(ctx, one, grid, leaf0, n / P, bc, x, xtmp, 0.5 * tau, gen_points, virt);
           if (rc == TBSLAS_OK) {
             done = true;
@@ -792,6 +793,7 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
     ctx->opt.locate_no_boxes = flag("TBSLAS_LOCATE_NO_BOXES", false);
     ctx->opt.tensor_generic = flag("TBSLAS_TENSOR_GENERIC", false);
     if (const char *e = getenv("TBSLAS_TENSOR_DMMA")) ctx->opt.tensor_dmma = atoi(e);
+    if (const char *e = getenv("TBSLAS_VIRTUAL_X")) ctx->virtual_x = atoi(e) != 0;  // = tbslas_b200_set_virtual_arrival_points
     if (const char *e = getenv("TBSLAS_TENSOR_CTAS")) ctx->opt.tensor_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 0;
     if (const char *e = getenv("TBSLAS_EVAL_VARIANT")) ctx->opt.eval_variant = atoi(e);
     if (const char *e = getenv("TBSLAS_EXCHANGE")) ctx->opt.peer_exchange = strcmp(e, "nccl") != 0;

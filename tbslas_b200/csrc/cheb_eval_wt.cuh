@@ -78,6 +78,7 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
   extern __shared__ __align__(128) double s_all[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_cend;
+  __shared__ double s_node[EPI == EPI_AXPY_GRID ? D : 1];  // the grid's 1-D nodes (grid-base epilogue)
   double *const s_coef = s_all;                       // [stride]
   double *const s_x = s_all + p.stride;               // [3][TP]
   double *const s_g = s_x + 3 * TP;                   // [4]
@@ -91,6 +92,7 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
     s_ctl[CT_NEXT] = 0;
     s_cend = 0;
   }
+  if (EPI == EPI_AXPY_GRID && lane < D) s_node[lane] = gb.node[lane];
   __syncwarp();
   // the descriptor of the next tile of the stream goes into ring slot n % 3 (written by lane 0)
   auto describe_next = [&](unsigned n) {
@@ -204,7 +206,7 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
         cp_async_8(d + 2 * TP, bp + 2);
       }
       if (EPI == EPI_AXPY_GRID) {  // geometry of the grid leaf the point is a node of
-        const double4 *gp = gb.ggeom + (unsigned)i / gb.P;
+        const double4 *gp = gb.ggeom + (unsigned)i / (unsigned)(D * D * D);  // (the launcher checked gb.D == D)
         double *d = s_b + ((n & 1) * TP + o) * 4;
         cp_async_16(d, gp);
         cp_async_16(d + 2, reinterpret_cast<const double *>(gp) + 2);
@@ -296,7 +298,7 @@ cheb_eval_wt_kernel(const EvalParams p, unsigned *__restrict__ chunk_counter, un
             p.out[3 * i + l] = __dadd_rn(s_b[(n & 1) * 3 * TP + l * TP + o], __dmul_rn(p.alpha, u[s]));
           } else {  // the same with x0 rebuilt from its leaf's geometry and its node index
             const double4 g = *reinterpret_cast<const double4 *>(s_b + ((n & 1) * TP + o) * 4);
-            p.out[3 * i + l] = __dadd_rn(grid_base_coord(gb, g, (unsigned)i, l), __dmul_rn(p.alpha, u[s]));
+            p.out[3 * i + l] = __dadd_rn(grid_base_coord_ct<D>(gb.periodic, s_node, g, (unsigned)i, l), __dmul_rn(p.alpha, u[s]));
           }
         }
       }
@@ -337,6 +339,7 @@ int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
   GridBase gb;
   if (a.epilogue == EPI_AXPY_GRID) {
     if (!a.grid) return fail(ctx, TBSLAS_ERR_INVALID, "grid epilogue without a grid");
+    if ((int)a.grid->D != Q + 1) return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "grid epilogue: the grid's degree differs from the tree's");
     gb = *a.grid;
   }
   // every CTA (one warp) is a worker: no more workers than tiles, at most 8 per SM

@@ -26,4 +26,21 @@ __device__ __forceinline__ double grid_base_coord(const GridBase &gb, const doub
   return b;
 }
 
+// The same with the nodes per axis known at compile time (divisions by constants) and the node table in
+// shared memory (a lane-divergent index into the kernel's parameter space is replayed per distinct index):
+// what the evaluation kernel's RK2 epilogue uses.
+template <int D>
+__device__ __forceinline__ double grid_base_coord_ct(int periodic, const double *node, const double4 &g, unsigned i,
+                                                     int axis) {
+  constexpr unsigned P2 = D * D, P = P2 * D;
+  const unsigned r = i % P;
+  const unsigned pz = r / P2, rem = r - pz * P2, py = rem / D, px = rem - py * D;
+  const unsigned k = axis == 0 ? px : (axis == 1 ? py : pz);
+  const double c = axis == 0 ? g.x : (axis == 1 ? g.y : g.z);
+  const double len = __longlong_as_double((2047ll << 52) - __double_as_longlong(g.w));
+  double b = __dadd_rn(c, __dmul_rn(len, node[k]));  // gridpts.cu
+  if (periodic) b = wrap_periodic(b);
+  return b;
+}
+
 }  // namespace tb
