@@ -366,6 +366,6 @@ int launch_cheb_eval_q(tbslas_ctx *ctx, const EvalArgs &a) {
 #ifndef TB_PPT14
 #define TB_PPT14 2
 #endif
-constexpr int eval_ppt(int q) { return q <= 9 ? 4 : (q <= 12 ? 3 : TB_PPT14); }
+constexpr int eval_ppt(int q) { return q <= 9 ? 4 : (q <= 12 ? 3 : (q <= 14 ? TB_PPT14 : 2)); }
 
 }  // namespace tb

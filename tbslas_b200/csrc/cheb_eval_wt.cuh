@@ -342,34 +342,30 @@ int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
     if ((int)a.grid->D != Q + 1) return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "grid epilogue: the grid's degree differs from the tree's");
     gb = *a.grid;
   }
-  // every CTA (one warp) is a worker: no more workers than tiles, at most 8 per SM
-  size_t grid = a.max_tiles;
-  if (grid > (size_t)8 * ctx->n_sm) grid = (size_t)8 * ctx->n_sm;
-  if (grid == 0) return TBSLAS_OK;
-  // largest chunk of consecutive tiles (leaf locality); the kernel shrinks them towards the end
-  size_t chunk = a.max_tiles / (grid * 8);
-  chunk = chunk < 2 ? 2 : (chunk > 16 ? 16 : chunk);
-  if (a.epilogue == EPI_STORE) {
-    const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_STORE>(t);
-    auto k = cheb_eval_wt_kernel<Q, PPT, EPI_STORE>;
+  if (a.max_tiles == 0) return TBSLAS_OK;
+  // every CTA (one warp) is a worker: no more workers than tiles, and as many per SM as are resident
+  // together -- 8 up to 27 KB of shared memory per worker, fewer for larger coefficient blocks
+  auto launch = [&](auto k, size_t smem) -> int {
     if (smem > 48 * 1024)
       TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 8;
+    if (smem > 27 * 1024) {
+      TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWtThreads, smem));
+      if (per_sm < 1) return fail(ctx, TBSLAS_ERR_UNSUPPORTED, "evaluation kernel does not fit an SM (%zu bytes)", smem);
+      if (per_sm > 8) per_sm = 8;
+    }
+    size_t grid = a.max_tiles;
+    if (grid > (size_t)per_sm * ctx->n_sm) grid = (size_t)per_sm * ctx->n_sm;
+    // largest chunk of consecutive tiles (leaf locality); the kernel shrinks them towards the end
+    size_t chunk = a.max_tiles / (grid * 8);
+    chunk = chunk < 2 ? 2 : (chunk > 16 ? 16 : chunk);
     k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk, gb);
-  } else if (a.epilogue == EPI_AXPY) {
-    const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_AXPY>(t);
-    auto k = cheb_eval_wt_kernel<Q, PPT, EPI_AXPY>;
-    if (smem > 48 * 1024)
-      TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk, gb);
-  } else {
-    const size_t smem = eval_wt_smem_bytes<Q, PPT, EPI_AXPY_GRID>(t);
-    auto k = cheb_eval_wt_kernel<Q, PPT, EPI_AXPY_GRID>;
-    if (smem > 48 * 1024)
-      TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk, gb);
-  }
-  TB_CUDA(ctx, cudaGetLastError());
-  return TBSLAS_OK;
+    TB_CUDA(ctx, cudaGetLastError());
+    return TBSLAS_OK;
+  };
+  if (a.epilogue == EPI_STORE) return launch(cheb_eval_wt_kernel<Q, PPT, EPI_STORE>, eval_wt_smem_bytes<Q, PPT, EPI_STORE>(t));
+  if (a.epilogue == EPI_AXPY) return launch(cheb_eval_wt_kernel<Q, PPT, EPI_AXPY>, eval_wt_smem_bytes<Q, PPT, EPI_AXPY>(t));
+  return launch(cheb_eval_wt_kernel<Q, PPT, EPI_AXPY_GRID>, eval_wt_smem_bytes<Q, PPT, EPI_AXPY_GRID>(t));
 }
 
 }  // namespace tb

@@ -143,6 +143,46 @@ def test_gpu_eval_every_degree(ctx, port, q):
         assert rel_err(v, vo) < RTOL
 
 
+@pytest.mark.parametrize("q,dof", [(14, 4), (19, 6), (19, 8), (11, 7)])
+def test_gpu_eval_wide_dof(ctx, port, q, dof):
+    """Coefficient blocks too large for eight resident workers per SM: the persistent kernel runs with fewer
+    workers per SM (q 14 dof 4: 28 KB; q 19 dof 6: 81 KB), beyond 100 KB (q 19 dof 8) the degree-generic kernel
+    takes over.  Same leaves and values as the oracle either way."""
+    api = _api()
+    coord, dd = ftm.uniform_leaves(1)
+    ft = ftm.random_tree(coord, dd, q, dof, seed=7 * q + dof)
+    f = api.NodeFieldFunctor(ctx.tree(ft))
+    h = port.tree_create(ft)
+    pts = np.random.default_rng(q + dof).uniform(-0.01, 1.01, size=(9000, 3))
+    vo, lo, _ = port.eval_tree(h, dof, pts, 0)
+    v, leaf = f.eval_with_leaf(pts.copy(), 0)
+    assert np.array_equal(leaf, lo)
+    assert rel_err(v, vo) < RTOL
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_gpu_eval_kernel_variants_agree(port, variant, monkeypatch):
+    """The A/B kernels behind TBSLAS_EVAL_VARIANT (1: one tile per CTA, q 8 and 14; 2: the degree-generic kernel,
+    which keeps T_0 as data and the reference's loop order) against the oracle, in a context of their own (the
+    switch is read once, at tbslas_b200_init)."""
+    api = _api()
+    monkeypatch.setenv("TBSLAS_EVAL_VARIANT", variant)
+    own = api.Context(0)
+    try:
+        for q, dof in ((8, 3), (14, 1)):
+            coord, dd = ftm.uniform_leaves(2)
+            ft = ftm.random_tree(coord, dd, q, dof, seed=q)
+            f = api.NodeFieldFunctor(own.tree(ft))
+            h = port.tree_create(ft)
+            pts = np.random.default_rng(q).uniform(-0.01, 1.01, size=(7000, 3))
+            vo, lo, _ = port.eval_tree(h, dof, pts, 0)
+            v, leaf = f.eval_with_leaf(pts.copy(), 0)
+            assert np.array_equal(leaf, lo)
+            assert rel_err(v, vo) < RTOL
+    finally:
+        own.close()
+
+
 @pytest.mark.parametrize("q,dof,bc", [(8, 3, 0), (14, 1, 1), (4, 2, 1), (14, 3, 0)])
 def test_gpu_eval_adaptive_tree(ctx, port, q, dof, bc):
     api = _api()
