@@ -794,6 +794,7 @@ int tbslas_b200_init(int device, tbslas_ctx **out) {
     ctx->opt.tensor_generic = flag("TBSLAS_TENSOR_GENERIC", false);
     if (const char *e = getenv("TBSLAS_TENSOR_DMMA")) ctx->opt.tensor_dmma = atoi(e);
     if (const char *e = getenv("TBSLAS_VIRTUAL_X")) ctx->virtual_x = atoi(e) != 0;  // = tbslas_b200_set_virtual_arrival_points
+    if (const char *e = getenv("TBSLAS_HOST_CHUNKS")) ctx->host_chunks = atoi(e);     // = tbslas_b200_set_host_chunks
     if (const char *e = getenv("TBSLAS_TENSOR_CTAS")) ctx->opt.tensor_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 0;
     if (const char *e = getenv("TBSLAS_EVAL_VARIANT")) ctx->opt.eval_variant = atoi(e);
     if (const char *e = getenv("TBSLAS_EXCHANGE")) ctx->opt.peer_exchange = strcmp(e, "nccl") != 0;

@@ -1,4 +1,4 @@
-"""tools/e2e_sweep.py -- where does the tree-level host call's time go?  (C2, one GPU)
+"""tools/e2e_sweep.py -- where does the tree-level host call's time go?  (WORKLOAD=c2|c3|c5, one GPU)
 Sweeps the number of host chunks, prints wall time per call, the per-stage device times and
 raw PCIe copy rates.  Diagnostic only; results are summarised under profiles/."""
 import json
@@ -17,11 +17,11 @@ from tbslas_b200 import flat_tree as ftm  # noqa: E402
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 scale = int(os.environ.get("SCALE", "0"))
-wl = workloads.make("c2", dev, scale)
+wl = workloads.make(os.environ.get("WORKLOAD", "c2"), dev, scale)
 ctx = api.Context(0)
 ctx.set_stream(torch.cuda.current_stream())
-tcon, tvel = ctx.tree(wl.con), ctx.tree(wl.vel[0])
-vel = api.NodeFieldFunctor(tvel)
+tcon, tvels = ctx.tree(wl.con), [ctx.tree(v) for v in wl.vel]
+vel = api.NodeFieldFunctor(tvels[0]) if len(tvels) == 1 else api.FieldSetFunctor(tvels, wl.vel_times)
 n = wl.n_points
 h_vals = torch.empty((n, 1), dtype=torch.float64, pin_memory=True)
 nc = ftm.ncoef(wl.q)
