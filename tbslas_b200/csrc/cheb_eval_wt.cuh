@@ -357,7 +357,12 @@ int launch_cheb_eval_wt(tbslas_ctx *ctx, const EvalArgs &a) {
     size_t grid = a.max_tiles;
     if (grid > (size_t)per_sm * ctx->n_sm) grid = (size_t)per_sm * ctx->n_sm;
     // largest chunk of consecutive tiles (leaf locality); the kernel shrinks them towards the end
-    size_t chunk = a.max_tiles / (grid * 8);
+    // (an eighth of a worker's tiles -- or half of them when it has fewer than 32: every refill is a global atomic
+    // plus a search for the chunk's first leaf, which a small launch pays many times over.  C1, 20 tiles per
+    // worker: evaluation launches 0.449 -> 0.421 ms per step; half everywhere cost C2 0.6 ms in its launch over
+    // the tensor-grid exceptions, 57 tiles per worker)
+    const size_t per_worker = a.max_tiles / grid;
+    size_t chunk = per_worker / (per_worker < 32 ? 2 : 8);
     chunk = chunk < 2 ? 2 : (chunk > 16 ? 16 : chunk);
     k<<<(unsigned)grid, kWtThreads, smem, ctx->stream>>>(p, a.chunk_counter, (unsigned)chunk, gb);
     TB_CUDA(ctx, cudaGetLastError());
